@@ -1,0 +1,68 @@
+"""Build libguacho_gx.so in-tree with nvcc for sm_100a (no JIT cache, no torch extension).
+
+    python -m guacho_b200.build [--force]
+
+The kernels are compiled twice: a bit-comparison build (-fmad=false, matches the
+reference's no-FMA x86 arithmetic) and the production build (-fmad=true).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(HERE, "csrc", "build")
+LIB = os.path.join(HERE, "libguacho_gx.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libguacho_gx.so cannot be built (there is no CPU fallback)")
+
+
+def _sources():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))] + [
+        os.path.join(os.path.dirname(HERE), "include", "guacho_gx.h")]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(s) > t for s in _sources())
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    nvcc = _nvcc()
+    os.makedirs(BUILD, exist_ok=True)
+    jobs = [
+        ("gx_kernels_strict.o", "gx_kernels.cu", ["-fmad=false", "-DGX_FLAVOUR_STRICT"]),
+        ("gx_kernels_fast.o", "gx_kernels.cu", ["-fmad=true", "-DGX_FLAVOUR_FAST"]),
+        ("gx_api.o", "gx_api.cu", ["-fmad=false"]),
+    ]
+    procs = []
+    for obj, src, extra in jobs:
+        cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", os.path.join(BUILD, obj)]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(out)
+        if p.returncode:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + [os.path.join(BUILD, j[0]) for j in jobs] + ["-ldl"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,673 @@
+// gx_api.cu — C-ABI of libguacho_gx.so (see include/guacho_gx.h): solver object,
+// reference-layout <-> device-SoA conversion, ghost-cell boundaries, step driver,
+// NCCL halo exchange and CFL reduction.  No CPU fallback exists on any path.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/guacho_gx.h"
+#include "gx_kernels.cuh"
+
+using gx::Grid;
+using gx::StepArgs;
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(GX_ECUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// ---------------------------------------------------------------------------
+// NCCL through dlopen: a single-GPU host never needs libnccl to be present.
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+  if (g_nccl.ok) return GX_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) { g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
+  if (!g_nccl.lib) return fail(GX_ECOMM, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define LD(f) *(void**)(&g_nccl.f) = dlsym(g_nccl.lib, "nccl" #f); if (!g_nccl.f) return fail(GX_ECOMM, "libnccl lacks nccl" #f)
+  LD(GetUniqueId); LD(CommInitRank); LD(CommDestroy); LD(Send); LD(Recv); LD(AllReduce); LD(GroupStart); LD(GroupEnd); LD(GetErrorString);
+#undef LD
+  g_nccl.ok = true;
+  return GX_OK;
+}
+#define NCCL_TRY(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) return fail(GX_ECOMM, "%s failed: %s", #x, g_nccl.GetErrorString(r_)); } while (0)
+
+// ---------------------------------------------------------------------------
+struct TimedLaunch { int cls; cudaEvent_t a, b; };
+
+struct gx_solver {
+  gx_config cfg;
+  StepArgs A;
+  const gx::KernelTable* K = nullptr;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  double *U = nullptr, *UP = nullptr, *W = nullptr, *F = nullptr, *E = nullptr, *Temp = nullptr;
+  double* stage = nullptr; size_t stage_doubles = 0;         // AoS staging for layout conversion
+  double* halo_send[6] = {0, 0, 0, 0, 0, 0};                  // packed faces (multi-GPU)
+  double* halo_recv[6] = {0, 0, 0, 0, 0, 0};
+  size_t halo_doubles[3] = {0, 0, 0};
+  struct DevScalars { unsigned long long dtmin_bits; int err; int pad; }* dscal = nullptr;   // device
+  DevScalars* hscal = nullptr;                                // pinned host mirror
+  bool have_state = false;
+  double time = 0.0;
+  // block topology (mpi_cart_shift results; -1 = MPI_PROC_NULL)
+  int nb[3] = {1, 1, 1}, co[3] = {0, 0, 0};
+  int nbr[3][2] = {{-1, -1}, {-1, -1}, {-1, -1}};             // neighbour ranks [dir][low/high]
+  bool periodic[3] = {false, false, false};
+  int bc[3][2];
+  // comm
+  ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
+  // user functors
+  std::vector<gx_wind_sphere> spheres; gx_wind_sphere* d_spheres = nullptr;
+  gx_host_bc_fn host_bc = nullptr; void* host_bc_user = nullptr;
+  // diagnostics
+  long long launches = 0;
+  bool profiling = false;
+  std::vector<TimedLaunch> timed; std::vector<cudaEvent_t> evpool;
+  double cls_ms[gx::KC_COUNT] = {0}; long long cls_n[gx::KC_COUNT] = {0};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr; double last_ms = 0.0;
+};
+
+// profiling brackets: CUDA events on the solver's own stream around each launch group
+struct LaunchScope {
+  gx_solver* s; int cls; cudaEvent_t a = nullptr, b = nullptr;
+  LaunchScope(gx_solver* s_, int cls_, int n = 1) : s(s_), cls(cls_) {
+    s->launches += n;
+    if (s->profiling) {
+      auto get = [&]() { cudaEvent_t e; if (!s->evpool.empty()) { e = s->evpool.back(); s->evpool.pop_back(); } else cudaEventCreate(&e); return e; };
+      a = get(); b = get();
+      cudaEventRecord(a, s->stream);
+    }
+  }
+  ~LaunchScope() { if (s->profiling) { cudaEventRecord(b, s->stream); s->timed.push_back({cls, a, b}); } }
+};
+static void collect_timed(gx_solver* s) {
+  if (s->timed.empty()) return;
+  cudaStreamSynchronize(s->stream);
+  for (auto& t : s->timed) {
+    float ms = 0; cudaEventElapsedTime(&ms, t.a, t.b);
+    s->cls_ms[t.cls] += ms; s->cls_n[t.cls] += 1;
+    s->evpool.push_back(t.a); s->evpool.push_back(t.b);
+  }
+  s->timed.clear();
+}
+
+// ---------------------------------------------------------------------------
+// layout conversion kernels: reference AoS (var fastest) <-> device SoA, z-chunked
+__global__ void k_aos_to_soa(Grid g, int nvar, const double* __restrict__ aos, double* __restrict__ soa, int k0, int nk) {
+  // aos chunk: (nvar, nx+4, ny+4, nk) column-major, planes k0..k0+nk-1 (0-based padded index)
+  const int ii = blockIdx.x * blockDim.x + threadIdx.x;      // 0..nx+3
+  const int jj = blockIdx.y, kk = blockIdx.z;
+  if (ii >= g.nx + 4) return;
+  const long long a = (long long)nvar * (ii + (long long)(g.nx + 4) * (jj + (long long)(g.ny + 4) * kk));
+  const long long c = ((long long)(k0 + kk) * g.py + jj) * g.px + (ii - 1 + g.xo);
+  for (int q = 0; q < nvar; ++q) soa[q * g.vs + c] = aos[a + q];
+}
+__global__ void k_soa_to_aos(Grid g, int nvar, const double* __restrict__ soa, double* __restrict__ aos, int k0, int nk) {
+  const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+  const int jj = blockIdx.y, kk = blockIdx.z;
+  if (ii >= g.nx + 4) return;
+  const long long a = (long long)nvar * (ii + (long long)(g.nx + 4) * (jj + (long long)(g.ny + 4) * kk));
+  const long long c = ((long long)(k0 + kk) * g.py + jj) * g.px + (ii - 1 + g.xo);
+  for (int q = 0; q < nvar; ++q) aos[a + q] = soa[q * g.vs + c];
+}
+
+// ---------------------------------------------------------------------------
+// ghost-cell kernels.  A face "job" copies nl layers across one face of the block.
+//   mode 0: periodic wrap inside the block   dst -> dst +/- n
+//   mode 1: mirror (outflow / closed)        low: src = 1 - dst ; high: src = 2n+1 - dst
+// negvar: variable whose sign flips (closed walls), -1 for none.
+// Transverse extent: 1-nl .. n+nl in both transverse directions, which is 0..n+1 for the
+// one-layer boundaries (src/boundaries.f90:101-242) and the full array for boundaryII (:316-505).
+__global__ void k_bc_face(Grid g, int nvar, double* __restrict__ A, int dir, int side, int mode, int nl, int negvar) {
+  const int n[3] = {g.nx, g.ny, g.nz};
+  const int ta = dir == 0 ? 1 : 0, tb = dir == 2 ? 1 : 2;     // transverse axes (a fast)
+  const int a = (int)(blockIdx.x * blockDim.x + threadIdx.x) + 1 - nl;
+  const int b = (int)blockIdx.y + 1 - nl;
+  if (a > n[ta] + nl) return;
+  const int nd = n[dir];
+  for (int l = 0; l < nl; ++l) {
+    const int dst = side == 0 ? (1 - nl + l) : (nd + 1 + l);
+    const int src = mode == 0 ? (side == 0 ? dst + nd : dst - nd) : (side == 0 ? 1 - dst : 2 * nd + 1 - dst);
+    int id[3], is[3];
+    id[dir] = dst; is[dir] = src; id[ta] = is[ta] = a; id[tb] = is[tb] = b;
+    const long long cd = g.idx(id[0], id[1], id[2]), cs = g.idx(is[0], is[1], is[2]);
+    for (int q = 0; q < nvar; ++q) {
+      const double v = A[q * g.vs + cs];
+      A[q * g.vs + cd] = (q == negvar) ? -v : v;
+    }
+  }
+}
+
+// pack / unpack a box [lo,hi] (Fortran indices, inclusive) of nvar variables to/from a contiguous buffer
+struct Box { int lo[3], hi[3]; };
+__global__ void k_pack(Grid g, int nvar, double* A, double* buf, Box bx, int unpack_flag) {
+  const int ex = bx.hi[0] - bx.lo[0] + 1, ey = bx.hi[1] - bx.lo[1] + 1;
+  const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ii >= ex) return;
+  const int jj = blockIdx.y, kk = blockIdx.z;
+  const long long c = g.idx(bx.lo[0] + ii, bx.lo[1] + jj, bx.lo[2] + kk);
+  const long long per = (long long)ex * ey * (bx.hi[2] - bx.lo[2] + 1);
+  const long long p = ii + (long long)ex * (jj + (long long)ey * kk);
+  for (int q = 0; q < nvar; ++q) {
+    if (unpack_flag) A[q * g.vs + c] = buf[q * per + p];
+    else buf[q * per + p] = A[q * g.vs + c];
+  }
+}
+
+// impose_user_bc functor: wind spheres (EXO/exoplanet.f90:125-266).  First matching sphere wins
+// (the reference tests the star first, then `else if` the planet).
+__global__ void k_wind_spheres(Grid g, gxp::Phys P, int mhd, const gx_wind_sphere* __restrict__ sph, int nsph, double* __restrict__ A) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) - 1;
+  const int j = (int)blockIdx.y - 1, k = (int)blockIdx.z - 1;
+  if (i > g.nx + 2) return;
+  const double x = ((double)(i + g.cx * g.nx - g.nxtot / 2) + 0.5) * g.dx;
+  const double y = ((double)(j + g.cy * g.ny - g.nytot / 2) + 0.5) * g.dy;
+  const double z = ((double)(k + g.cz * g.nz - g.nztot / 2) + 0.5) * g.dz;
+  const long long c = g.idx(i, j, k);
+  for (int m = 0; m < nsph; ++m) {
+    const gx_wind_sphere& S = sph[m];
+    const double xl = x - S.xc, yl = y - S.yc, zl = z - S.zc;
+    double rad = sqrt(xl * xl + yl * yl + zl * zl);
+    if (rad <= S.radius) {
+      if (rad == 0.) rad = g.dx * 0.10;
+      const double velx = S.vbx + S.vwind * xl / rad, vely = S.vby + S.vwind * yl / rad, velz = S.vbz + S.vwind * zl / rad;
+      const double dens = S.dens;
+      A[0 * g.vs + c] = dens;
+      A[1 * g.vs + c] = dens * velx;
+      A[2 * g.vs + c] = dens * vely;
+      A[3 * g.vs + c] = dens * velz;
+      double b2h = 0.0;
+      if (g.neqdyn == 8) {
+        const double q3 = S.radius / rad;
+        const double cpi = S.bdip * (q3 * q3 * q3) / (2. * (rad * rad));
+        const double bx = 3. * yl * xl * cpi, by = (3. * (yl * yl) - rad * rad) * cpi, bz = 3. * yl * zl * cpi;
+        A[5 * g.vs + c] = bx; A[6 * g.vs + c] = by; A[7 * g.vs + c] = bz;
+        b2h = 0.5 * (bx * bx + by * by + bz * bz);
+      }
+      double e = 0.5 * dens * (velx * velx + vely * vely + velz * velz) + P.cv * dens * S.temp_eff;
+      if (mhd) e = e + b2h;
+      A[4 * g.vs + c] = e;
+      for (int q = 0; q < g.npas && q < 4; ++q) A[(long long)(g.neqdyn + q) * g.vs + c] = S.pas[q] * dens;
+      return;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+static int upload_aos(gx_solver* s, const double* host, double* soa, int nvar) {
+  const Grid& g = s->A.g;
+  const size_t plane = (size_t)nvar * (g.nx + 4) * (g.ny + 4);
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(g.nz + 4, s->stage_doubles / plane));
+  for (int k0 = 0; k0 < g.nz + 4; k0 += chunk) {
+    const int nk = std::min(chunk, g.nz + 4 - k0);
+    CUDA_TRY(cudaMemcpyAsync(s->stage, host + plane * k0, plane * nk * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    LaunchScope ls(s, gx::KC_XPOSE);
+    k_aos_to_soa<<<dim3((g.nx + 4 + 127) / 128, g.ny + 4, nk), 128, 0, s->stream>>>(g, nvar, s->stage, soa, k0, nk);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return GX_OK;
+}
+static int download_aos(gx_solver* s, const double* soa, double* host, int nvar) {
+  const Grid& g = s->A.g;
+  const size_t plane = (size_t)nvar * (g.nx + 4) * (g.ny + 4);
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(g.nz + 4, s->stage_doubles / plane));
+  for (int k0 = 0; k0 < g.nz + 4; k0 += chunk) {
+    const int nk = std::min(chunk, g.nz + 4 - k0);
+    {
+      LaunchScope ls(s, gx::KC_XPOSE);
+      k_soa_to_aos<<<dim3((g.nx + 4 + 127) / 128, g.ny + 4, nk), 128, 0, s->stream>>>(g, nvar, soa, s->stage, k0, nk);
+    }
+    CUDA_TRY(cudaMemcpyAsync(host + plane * k0, s->stage, plane * nk * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));   // staging buffer is reused by the next chunk
+  }
+  CUDA_TRY(cudaGetLastError());
+  return GX_OK;
+}
+
+// ---- halo exchange between blocks (replaces the six mpi_sendrecv of each boundary routine) ----
+static Box face_box(const Grid& g, int dir, int side, int nl, bool ghost) {
+  // ghost=false: the nl physical layers adjacent to the face; ghost=true: the nl ghost layers beyond it
+  const int n[3] = {g.nx, g.ny, g.nz};
+  Box b;
+  for (int d = 0; d < 3; ++d) { b.lo[d] = 1 - nl; b.hi[d] = n[d] + nl; }
+  if (!ghost) { b.lo[dir] = side == 0 ? 1 : n[dir] - nl + 1; b.hi[dir] = side == 0 ? nl : n[dir]; }
+  else { b.lo[dir] = side == 0 ? 1 - nl : n[dir] + 1; b.hi[dir] = side == 0 ? 0 : n[dir] + nl; }
+  return b;
+}
+static size_t box_cells(const Box& b) { return (size_t)(b.hi[0] - b.lo[0] + 1) * (b.hi[1] - b.lo[1] + 1) * (b.hi[2] - b.lo[2] + 1); }
+static void launch_pack(gx_solver* s, int nvar, double* A, double* buf, const Box& b, int unpack) {
+  LaunchScope ls(s, gx::KC_BC);
+  dim3 grid((b.hi[0] - b.lo[0] + 1 + 63) / 64, b.hi[1] - b.lo[1] + 1, b.hi[2] - b.lo[2] + 1);
+  k_pack<<<grid, 64, 0, s->stream>>>(s->A.g, nvar, A, buf, b, unpack);
+}
+
+static int exchange_dir(gx_solver* s, double* A, int nvar, int nl, int dir) {
+  // all faces are packed before anything is received, like the reference (boundaries.f90:70-75)
+  const Grid& g = s->A.g;
+  const int lo = s->nbr[dir][0], hi = s->nbr[dir][1];
+  if (lo < 0 && hi < 0) return GX_OK;
+  if (!s->comm) return fail(GX_ECOMM, "block has neighbours but no communicator is attached (gx_comm_attach)");
+  const Box sb_lo = face_box(g, dir, 0, nl, false), sb_hi = face_box(g, dir, 1, nl, false);
+  const size_t cnt = box_cells(sb_lo) * nvar;
+  if (cnt > s->halo_doubles[dir]) return fail(GX_ESTATE, "halo buffer too small");
+  double *send_lo = s->halo_send[2 * dir], *send_hi = s->halo_send[2 * dir + 1];
+  double *recv_lo = s->halo_recv[2 * dir], *recv_hi = s->halo_recv[2 * dir + 1];
+  if (lo >= 0) launch_pack(s, nvar, A, send_lo, sb_lo, 0);
+  if (hi >= 0) launch_pack(s, nvar, A, send_hi, sb_hi, 0);
+  NCCL_TRY(g_nccl.GroupStart());
+  if (hi >= 0) { NCCL_TRY(g_nccl.Send(send_hi, cnt, ncclDouble, hi, s->comm, s->stream)); NCCL_TRY(g_nccl.Recv(recv_hi, cnt, ncclDouble, hi, s->comm, s->stream)); }
+  if (lo >= 0) { NCCL_TRY(g_nccl.Send(send_lo, cnt, ncclDouble, lo, s->comm, s->stream)); NCCL_TRY(g_nccl.Recv(recv_lo, cnt, ncclDouble, lo, s->comm, s->stream)); }
+  NCCL_TRY(g_nccl.GroupEnd());
+  if (lo >= 0) launch_pack(s, nvar, A, recv_lo, face_box(g, dir, 0, nl, true), 1);
+  if (hi >= 0) launch_pack(s, nvar, A, recv_hi, face_box(g, dir, 1, nl, true), 1);
+  return GX_OK;
+}
+
+static void launch_bc_face(gx_solver* s, double* A, int nvar, int dir, int side, int mode, int nl, int negvar) {
+  const Grid& g = s->A.g;
+  const int n[3] = {g.nx, g.ny, g.nz};
+  const int ta = dir == 0 ? 1 : 0, tb = dir == 2 ? 1 : 2;
+  LaunchScope ls(s, gx::KC_BC);
+  dim3 grid((n[ta] + 2 * nl + 63) / 64, n[tb] + 2 * nl);
+  k_bc_face<<<grid, 64, 0, s->stream>>>(g, nvar, A, dir, side, mode, nl, negvar);
+}
+
+// kind 0: conserved/primitive array (closed wall flips normal momentum, boundaries.f90:146-199, 361-438)
+// kind 1: electric field (closed wall flips e(1) on x walls, e(2) on y walls, nothing on z walls,
+//         flux_cd_module.f90:143-192)
+static int apply_boundaries(gx_solver* s, double* A, int nvar, int nl, int kind) {
+  for (int dir = 0; dir < 3; ++dir) {
+    if (s->nb[dir] == 1 && s->periodic[dir]) {            // neighbour is the block itself
+      launch_bc_face(s, A, nvar, dir, 0, 0, nl, -1);
+      launch_bc_face(s, A, nvar, dir, 1, 0, nl, -1);
+    } else {
+      int rc = exchange_dir(s, A, nvar, nl, dir);
+      if (rc) return rc;
+    }
+  }
+  for (int pass = 0; pass < 2; ++pass) {                   // closed first, then outflow (reference order)
+    const int want = pass == 0 ? GX_BC_CLOSED : GX_BC_OUTFLOW;
+    for (int dir = 0; dir < 3; ++dir)
+      for (int side = 0; side < 2; ++side) {
+        if (s->bc[dir][side] != want) continue;
+        if (s->co[dir] != (side == 0 ? 0 : s->nb[dir] - 1)) continue;   // only blocks on the domain edge
+        int negvar = -1;
+        if (want == GX_BC_CLOSED) negvar = kind == 0 ? 1 + dir : (dir == 2 ? -1 : dir);
+        launch_bc_face(s, A, nvar, dir, side, 1, nl, negvar);
+      }
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(GX_ECUDA, "boundary kernel launch: %s", cudaGetErrorString(e));
+  return GX_OK;
+}
+
+static int apply_user_bc(gx_solver* s, double* A, int order) {
+  if (!s->cfg.bc_user) return GX_OK;
+  const Grid& g = s->A.g;
+  if (!s->spheres.empty()) {
+    LaunchScope ls(s, gx::KC_BC);
+    k_wind_spheres<<<dim3((g.nx + 4 + 127) / 128, g.ny + 4, g.nz + 4), 128, 0, s->stream>>>(g, s->A.phys, s->cfg.mhd, s->d_spheres, (int)s->spheres.size(), A);
+  }
+  if (s->host_bc) {   // slow path: device -> host -> callback -> device
+    std::vector<double> h((size_t)g.neq * (g.nx + 4) * (g.ny + 4) * (g.nz + 4));
+    int rc = download_aos(s, A, h.data(), g.neq); if (rc) return rc;
+    s->host_bc(h.data(), order, s->host_bc_user);
+    rc = upload_aos(s, h.data(), A, g.neq); if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+  }
+  return GX_OK;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char* gx_last_error(void) { return g_err.c_str(); }
+
+const char* gx_build_info(void) {
+  return "libguacho_gx sm_100a; kernels: strict(-fmad=false) + fast(-fmad=true); FP64; built " __DATE__;
+}
+
+int gx_create(const gx_config* c, gx_solver** out) {
+  if (!c || !out) return fail(GX_EINVAL, "null argument");
+  *out = nullptr;
+  if (c->struct_bytes != (int)sizeof(gx_config)) return fail(GX_EINVAL, "gx_config size mismatch: caller %d, library %d", c->struct_bytes, (int)sizeof(gx_config));
+  if (c->nghost != 2) return fail(GX_EINVAL, "nghost must be 2 (parameters.f90:193)");
+  if (c->nbx < 1 || c->nby < 1 || c->nbz < 1) return fail(GX_EINVAL, "bad block grid");
+  if (c->nxtot % c->nbx || c->nytot % c->nby || c->nztot % c->nbz) return fail(GX_EINVAL, "grid not divisible by block grid");
+  const int nx = c->nxtot / c->nbx, ny = c->nytot / c->nby, nz = c->nztot / c->nbz;
+  if (nx < 2 || ny < 2 || nz < 2) return fail(GX_EINVAL, "each block needs >= 2 cells per direction");
+  if (c->cx < 0 || c->cx >= c->nbx || c->cy < 0 || c->cy >= c->nby || c->cz < 0 || c->cz >= c->nbz) return fail(GX_EINVAL, "block coords outside block grid");
+  if (c->neqdyn != 5 && c->neqdyn != 8) return fail(GX_EINVAL, "neqdyn must be 5 or 8");
+  if (c->neq != c->neqdyn + c->npas || c->npas < 0) return fail(GX_EINVAL, "neq != neqdyn + npas");
+  if (c->pmhd) return fail(GX_EUNSUPPORTED, "passive-MHD (pmhd) is not implemented on the device path");
+  const bool mhd_solver = c->riemann_solver == GX_SOLVER_HLLE || c->riemann_solver == GX_SOLVER_HLLD;
+  const bool hd_solver = c->riemann_solver == GX_SOLVER_HLL || c->riemann_solver == GX_SOLVER_HLLC;
+  if (!mhd_solver && !hd_solver) return fail(GX_EUNSUPPORTED, "riemann_solver %d not implemented (split variants have no reference implementation either)", c->riemann_solver);
+  if (mhd_solver && !(c->mhd && c->neqdyn == 8)) return fail(GX_EINVAL, "HLLE/HLLD need mhd=1, neqdyn=8");
+  if (hd_solver && (c->mhd || c->neqdyn != 5)) return fail(GX_EINVAL, "HLL/HLLC use hydro wave speeds: run with mhd=0, neqdyn=5 (SURVEY Q12)");
+  if (c->enable_flux_cd && !c->mhd) return fail(GX_EINVAL, "flux-CD without B field updates nothing (hydro_solver.f90:103-113)");
+  if (c->slope_limiter < -1 || c->slope_limiter > 6) return fail(GX_EINVAL, "unknown slope limiter");
+  if (c->eq_of_state == GX_EOS_CHEM) return fail(GX_EUNSUPPORTED, "EOS_CHEM needs the chemistry network (out of scope)");
+  const int bcs[6] = {c->bc_left, c->bc_right, c->bc_bottom, c->bc_top, c->bc_out, c->bc_in};
+  for (int b : bcs) if (b < GX_BC_OUTFLOW || b > GX_BC_OTHER) return fail(GX_EINVAL, "unknown boundary condition %d", b);
+  if (!(c->dx > 0 && c->dy > 0 && c->dz > 0 && c->cv > 0 && c->gamma > 0)) return fail(GX_EINVAL, "dx, dy, dz, cv, gamma must be positive");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(GX_ENODEVICE, "no CUDA device: the step has no CPU fallback"); }
+  gx_solver* s = new gx_solver();
+  s->cfg = *c;
+  if (c->device >= 0) { if (c->device >= ndev) { delete s; return fail(GX_ENODEVICE, "device %d of %d", c->device, ndev); } s->device = c->device; cudaSetDevice(s->device); }
+  else cudaGetDevice(&s->device);
+
+  Grid& g = s->A.g;
+  g.nx = nx; g.ny = ny; g.nz = nz;
+  g.xo = 15;
+  g.px = ((nx + 2 + g.xo + 1) + 15) / 16 * 16;
+  g.py = ny + 4; g.pz = nz + 4;
+  g.vs = (long long)g.px * g.py * g.pz;
+  g.neq = c->neq; g.neqdyn = c->neqdyn; g.npas = c->npas;
+  g.cx = c->cx; g.cy = c->cy; g.cz = c->cz;
+  g.nxtot = c->nxtot; g.nytot = c->nytot; g.nztot = c->nztot;
+  g.dx = c->dx; g.dy = c->dy; g.dz = c->dz;
+  s->A.phys.cv = c->cv; s->A.phys.gamma = c->gamma; s->A.phys.Tempsc = c->Tempsc;
+  s->A.phys.eos = c->eq_of_state; s->A.phys.neqdyn = c->neqdyn; s->A.phys.npas = c->npas;
+  s->A.solver = c->riemann_solver; s->A.limiter = c->slope_limiter;
+  s->A.flux_cd = c->enable_flux_cd; s->A.eight_wave = c->eight_wave; s->A.user_src = c->user_source_terms;
+  s->A.grav.n = 0;
+  s->K = c->strict_fp ? gx::kernels_strict() : gx::kernels_fast();
+
+  s->nb[0] = c->nbx; s->nb[1] = c->nby; s->nb[2] = c->nbz;
+  s->co[0] = c->cx; s->co[1] = c->cy; s->co[2] = c->cz;
+  for (int d = 0; d < 3; ++d) { s->bc[d][0] = bcs[2 * d]; s->bc[d][1] = bcs[2 * d + 1]; s->periodic[d] = (bcs[2 * d] == GX_BC_PERIODIC && bcs[2 * d + 1] == GX_BC_PERIODIC); }
+  auto rank_of = [&](int x, int y, int z) { return (x * c->nby + y) * c->nbz + z; };
+  for (int d = 0; d < 3; ++d)
+    for (int side = 0; side < 2; ++side) {
+      int cc[3] = {c->cx, c->cy, c->cz};
+      cc[d] += side == 0 ? -1 : 1;
+      if (cc[d] < 0 || cc[d] >= s->nb[d]) { if (!s->periodic[d]) { s->nbr[d][side] = -1; continue; } cc[d] = (cc[d] + s->nb[d]) % s->nb[d]; }
+      s->nbr[d][side] = (s->nb[d] == 1) ? -1 : rank_of(cc[0], cc[1], cc[2]);   // self-neighbour handled locally
+    }
+  s->rank = rank_of(c->cx, c->cy, c->cz);
+
+#define ALLOC(p, n) do { cudaError_t e_ = cudaMalloc((void**)&(p), (n)); if (e_ != cudaSuccess) { std::string m = cudaGetErrorString(e_); gx_destroy(s); return fail(GX_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", (size_t)(n), m.c_str()); } cudaMemsetAsync((p), 0, (n), 0); } while (0)
+  cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  const size_t var_bytes = (size_t)g.vs * sizeof(double);
+  ALLOC(s->U, var_bytes * g.neq);
+  ALLOC(s->UP, var_bytes * g.neq);
+  ALLOC(s->W, var_bytes * g.neq);
+  ALLOC(s->F, var_bytes * g.neq * 3);
+  if (c->enable_flux_cd) ALLOC(s->E, var_bytes * 3);
+  ALLOC(s->dscal, sizeof(gx_solver::DevScalars));
+  cudaMallocHost((void**)&s->hscal, sizeof(gx_solver::DevScalars));
+  // staging: up to 64 MiB or 4 planes, whichever is larger
+  const size_t plane = (size_t)g.neq * (g.nx + 4) * (g.ny + 4);
+  s->stage_doubles = std::max(plane * 4, std::min(plane * (size_t)(g.nz + 4), (size_t)(64u << 20) / sizeof(double)));
+  s->stage_doubles = std::min(s->stage_doubles, plane * (size_t)(g.nz + 4));
+  ALLOC(s->stage, s->stage_doubles * sizeof(double));
+  // halo buffers only where a real neighbour exists
+  const int n3[3] = {nx, ny, nz};
+  for (int d = 0; d < 3; ++d) {
+    if (s->nbr[d][0] < 0 && s->nbr[d][1] < 0) continue;
+    size_t cells = 2;   // nl = 2 layers, full transverse extent
+    for (int t = 0; t < 3; ++t) if (t != d) cells *= (size_t)(n3[t] + 4);
+    s->halo_doubles[d] = cells * g.neq;
+    for (int side = 0; side < 2; ++side) { ALLOC(s->halo_send[2 * d + side], s->halo_doubles[d] * sizeof(double)); ALLOC(s->halo_recv[2 * d + side], s->halo_doubles[d] * sizeof(double)); }
+  }
+#undef ALLOC
+  cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { gx_destroy(s); return fail(GX_ECUDA, "device sync after allocation: %s", cudaGetErrorString(e)); }
+  *out = s;
+  return GX_OK;
+}
+
+int gx_destroy(gx_solver* s) {
+  if (!s) return GX_OK;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->comm && g_nccl.ok) g_nccl.CommDestroy(s->comm);
+  double* ptrs[] = {s->U, s->UP, s->W, s->F, s->E, s->Temp, s->stage};
+  for (double* p : ptrs) if (p) cudaFree(p);
+  for (int q = 0; q < 6; ++q) { if (s->halo_send[q]) cudaFree(s->halo_send[q]); if (s->halo_recv[q]) cudaFree(s->halo_recv[q]); }
+  if (s->dscal) cudaFree(s->dscal);
+  if (s->hscal) cudaFreeHost(s->hscal);
+  if (s->d_spheres) cudaFree(s->d_spheres);
+  for (auto e : s->evpool) cudaEventDestroy(e);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return GX_OK;
+}
+
+static int reset_scalars(gx_solver* s) {
+  gx_solver::DevScalars init; init.dtmin_bits = 0x7FF0000000000000ull; init.err = 0; init.pad = 0;   // +inf
+  *s->hscal = init;
+  CUDA_TRY(cudaMemcpyAsync(s->dscal, s->hscal, sizeof init, cudaMemcpyHostToDevice, s->stream));
+  return GX_OK;
+}
+
+// boundaryI + calcprim(u, primit) (+ CFL candidates for the next get_timestep)
+static int finish_u(gx_solver* s) {
+  int rc = apply_boundaries(s, s->U, s->A.g.neq, 1, 0); if (rc) return rc;
+  rc = apply_user_bc(s, s->U, 1); if (rc) return rc;
+  rc = reset_scalars(s); if (rc) return rc;
+  { LaunchScope ls(s, gx::KC_PRIM); s->K->calcprim(s->A, s->U, s->W, nullptr, &s->dscal->dtmin_bits, 1, s->stream); }
+  CUDA_TRY(cudaGetLastError());
+  return GX_OK;
+}
+
+int gx_set_state(gx_solver* s, const double* u) {
+  if (!s || !u) return fail(GX_EINVAL, "null argument");
+  cudaSetDevice(s->device);
+  int rc = upload_aos(s, u, s->U, s->A.g.neq); if (rc) return rc;
+  rc = finish_u(s); if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  collect_timed(s);
+  s->have_state = true;
+  return GX_OK;
+}
+
+int gx_set_time(gx_solver* s, double time) { if (!s) return fail(GX_EINVAL, "null"); s->time = time; return GX_OK; }
+
+int gx_get_timestep(gx_solver* s, int32_t current_iter, int32_t n_iter, double current_time, double tprint, double* dt, int32_t* dump_flag) {
+  if (!s || !dt) return fail(GX_EINVAL, "null argument");
+  if (!s->have_state) return fail(GX_ESTATE, "gx_set_state has not been called");
+  cudaSetDevice(s->device);
+  if (s->comm && s->nranks > 1) {   // mpi_allreduce(MIN) (hydro_core.f90:685); min of positive doubles == min of bit patterns
+    NCCL_TRY(g_nccl.AllReduce(&s->dscal->dtmin_bits, &s->dscal->dtmin_bits, 1, ncclUint64, ncclMin, s->comm, s->stream));
+  }
+  CUDA_TRY(cudaMemcpyAsync(s->hscal, s->dscal, sizeof(gx_solver::DevScalars), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (s->hscal->err) return fail(GX_ENUMERIC, "Riemann solver fell through every branch (NaN state): the reference prints 'Error in HLLD routine' and stops");
+  double dtp; memcpy(&dtp, &s->hscal->dtmin_bits, sizeof dtp);
+  dtp = std::min(dtp, 1.e30);                                            // hydro_core.f90:642
+  // the ramp multiplies by exact powers of two, so applying it after the global min is
+  // bit-identical to the reference's per-rank application before mpi_allreduce (:677-685)
+  if (current_iter <= n_iter) dtp = s->cfg.cfl * pow(2., -(double)(n_iter + 1 - current_iter)) * dtp;
+  else dtp = s->cfg.cfl * dtp;
+  if ((current_time + dtp) >= tprint) { dtp = tprint - current_time; if (dump_flag) *dump_flag = 1; }
+  *dt = dtp;
+  return GX_OK;
+}
+
+static int tstep_enqueue(gx_solver* s, double dt_cfl) {
+  const gx::KernelTable* K = s->K;
+  const StepArgs& A = s->A;
+  const int neq = A.g.neq;
+  const double dtm = dt_cfl / 2.;                                        // hydro_solver.f90:152
+  int rc;
+  { LaunchScope ls(s, gx::KC_FLUX, 3); rc = K->fluxes(A, 1, s->W, s->F, &s->dscal->err, s->stream); } if (rc) return fail(rc, "flux launch");
+  if (A.flux_cd) {
+    { LaunchScope ls(s, gx::KC_EFIELD); K->efield(A, s->F, s->E, s->stream); }
+    rc = apply_boundaries(s, s->E, 3, 1, 1); if (rc) return rc;
+  }
+  { LaunchScope ls(s, gx::KC_UPDATE); K->update(A, dtm, s->U, s->F, s->E, s->W, s->UP, s->stream); }      // step(dtm) :165
+  rc = apply_boundaries(s, s->UP, neq, 2, 0); if (rc) return rc;          // boundaryII :169
+  rc = apply_user_bc(s, s->UP, 2); if (rc) return rc;
+  { LaunchScope ls(s, gx::KC_PRIM); K->calcprim(A, s->UP, s->W, nullptr, nullptr, 0, s->stream); }        // :170
+  { LaunchScope ls(s, gx::KC_FLUX, 3); rc = K->fluxes(A, 2, s->W, s->F, &s->dscal->err, s->stream); } if (rc) return fail(rc, "flux launch");
+  if (A.flux_cd) {
+    { LaunchScope ls(s, gx::KC_EFIELD); K->efield(A, s->F, s->E, s->stream); }
+    rc = apply_boundaries(s, s->E, 3, 1, 1); if (rc) return rc;
+  }
+  if (s->cfg.eta == 0.0) {
+    // viscous_copy with eta = 0 is u(interior) = up(interior): write the full step straight into u
+    { LaunchScope ls(s, gx::KC_UPDATE); K->update(A, dt_cfl, s->U, s->F, s->E, s->W, s->U, s->stream); }
+  } else {
+    { LaunchScope ls(s, gx::KC_UPDATE); K->update(A, dt_cfl, s->U, s->F, s->E, s->W, s->UP, s->stream); } // step(dt) :184
+    { LaunchScope ls(s, gx::KC_VISC); K->viscous(A, s->cfg.eta, s->UP, s->U, s->stream); }                // :188 (stale half-step ghosts of up)
+  }
+  rc = finish_u(s); if (rc) return rc;                                    // boundaryI :216, calcprim :218-224
+  CUDA_TRY(cudaGetLastError());
+  return GX_OK;
+}
+
+int gx_tstep(gx_solver* s, double dt_cfl) {
+  if (!s) return fail(GX_EINVAL, "null argument");
+  if (!s->have_state) return fail(GX_ESTATE, "gx_set_state has not been called");
+  cudaSetDevice(s->device);
+  CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+  int rc = tstep_enqueue(s, dt_cfl); if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, s->ev0, s->ev1); s->last_ms = ms;
+  collect_timed(s);
+  return GX_OK;
+}
+
+int gx_run(gx_solver* s, int32_t n_steps, int32_t n_iter_ramp, double* time, int32_t* iter, double* last_dt) {
+  if (!s || !time || !iter) return fail(GX_EINVAL, "null argument");
+  if (!s->have_state) return fail(GX_ESTATE, "gx_set_state has not been called");
+  cudaSetDevice(s->device);
+  CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+  for (int n = 0; n < n_steps; ++n) {
+    double dt; int32_t dump = 0;
+    int rc = gx_get_timestep(s, *iter, n_iter_ramp, *time, 1.e300, &dt, &dump); if (rc) return rc;
+    s->time = *time;
+    rc = tstep_enqueue(s, dt); if (rc) return rc;
+    *time += dt; *iter += 1;
+    if (last_dt) *last_dt = dt;
+  }
+  CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, s->ev0, s->ev1); s->last_ms = ms;
+  collect_timed(s);
+  return GX_OK;
+}
+
+int gx_get_state(gx_solver* s, double* u, double* primit, double* temp) {
+  if (!s) return fail(GX_EINVAL, "null argument");
+  if (!s->have_state) return fail(GX_ESTATE, "gx_set_state has not been called");
+  cudaSetDevice(s->device);
+  const Grid& g = s->A.g;
+  int rc;
+  if (u) { rc = download_aos(s, s->U, u, g.neq); if (rc) return rc; }
+  if (primit) { rc = download_aos(s, s->W, primit, g.neq); if (rc) return rc; }
+  if (temp) {
+    if (!s->Temp) { CUDA_TRY(cudaMalloc((void**)&s->Temp, (size_t)g.vs * sizeof(double))); CUDA_TRY(cudaMemsetAsync(s->Temp, 0, (size_t)g.vs * sizeof(double), s->stream)); }
+    { LaunchScope ls(s, gx::KC_PRIM); s->K->calcprim(s->A, s->U, s->W, s->Temp, nullptr, 0, s->stream); }
+    rc = download_aos(s, s->Temp, temp, 1); if (rc) return rc;
+  }
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  collect_timed(s);
+  return GX_OK;
+}
+
+int gx_get_up(gx_solver* s, double* up) {
+  if (!s || !up) return fail(GX_EINVAL, "null argument");
+  cudaSetDevice(s->device);
+  int rc = download_aos(s, s->UP, up, s->A.g.neq); if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return GX_OK;
+}
+
+int gx_set_gravity_points(gx_solver* s, int32_t n, const double* gm, const double* pos) {
+  if (!s || n < 0 || n > 4 || (n > 0 && (!gm || !pos))) return fail(GX_EINVAL, "0 <= n <= 4 point masses");
+  s->A.grav.n = n;
+  for (int l = 0; l < n; ++l) { s->A.grav.gm[l] = gm[l]; s->A.grav.x[l] = pos[3 * l]; s->A.grav.y[l] = pos[3 * l + 1]; s->A.grav.z[l] = pos[3 * l + 2]; }
+  return GX_OK;
+}
+
+int gx_set_wind_spheres(gx_solver* s, int32_t n, const gx_wind_sphere* sph) {
+  if (!s || n < 0 || (n > 0 && !sph)) return fail(GX_EINVAL, "bad arguments");
+  cudaSetDevice(s->device);
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  s->spheres.assign(sph, sph + n);
+  if (s->d_spheres) { cudaFree(s->d_spheres); s->d_spheres = nullptr; }
+  if (n > 0) {
+    CUDA_TRY(cudaMalloc((void**)&s->d_spheres, n * sizeof(gx_wind_sphere)));
+    CUDA_TRY(cudaMemcpy(s->d_spheres, sph, n * sizeof(gx_wind_sphere), cudaMemcpyHostToDevice));
+  }
+  return GX_OK;
+}
+
+int gx_register_host_bc(gx_solver* s, gx_host_bc_fn cb, void* user) {
+  if (!s) return fail(GX_EINVAL, "null argument");
+  s->host_bc = cb; s->host_bc_user = user;
+  return GX_OK;
+}
+
+int gx_comm_unique_id(void* id_out, int32_t nbytes) {
+  if (!id_out || nbytes < (int)sizeof(ncclUniqueId)) return fail(GX_EINVAL, "id buffer must hold %d bytes", (int)sizeof(ncclUniqueId));
+  int rc = nccl_load(); if (rc) return rc;
+  ncclUniqueId id;
+  NCCL_TRY(g_nccl.GetUniqueId(&id));
+  memcpy(id_out, &id, sizeof id);
+  return GX_OK;
+}
+
+int gx_comm_attach(gx_solver* s, const void* idp, int32_t nbytes, int32_t rank, int32_t nranks) {
+  if (!s || !idp || nbytes < (int)sizeof(ncclUniqueId)) return fail(GX_EINVAL, "bad arguments");
+  if (nranks != s->nb[0] * s->nb[1] * s->nb[2]) return fail(GX_EINVAL, "communicator size %d != number of blocks %d", nranks, s->nb[0] * s->nb[1] * s->nb[2]);
+  if (rank != s->rank) return fail(GX_EINVAL, "rank %d does not own block coords (%d,%d,%d) = rank %d", rank, s->co[0], s->co[1], s->co[2], s->rank);
+  int rc = nccl_load(); if (rc) return rc;
+  cudaSetDevice(s->device);
+  ncclUniqueId id; memcpy(&id, idp, sizeof id);
+  NCCL_TRY(g_nccl.CommInitRank(&s->comm, nranks, id, rank));
+  s->nranks = nranks;
+  return GX_OK;
+}
+
+int64_t gx_launch_count(const gx_solver* s) { return s ? s->launches : 0; }
+double gx_last_elapsed_ms(const gx_solver* s) { return s ? s->last_ms : 0.0; }
+int gx_set_profiling(gx_solver* s, int32_t on) {
+  if (!s) return fail(GX_EINVAL, "null argument");
+  collect_timed(s);
+  s->profiling = on != 0;
+  for (int c = 0; c < gx::KC_COUNT; ++c) { s->cls_ms[c] = 0; s->cls_n[c] = 0; }
+  return GX_OK;
+}
+int gx_kernel_time_ms(const gx_solver* s, int32_t which, double* total_ms, int64_t* launches) {
+  if (!s || which < 0 || which >= gx::KC_COUNT) return fail(GX_EINVAL, "bad kernel class");
+  if (total_ms) *total_ms = s->cls_ms[which];
+  if (launches) *launches = s->cls_n[which];
+  return GX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,283 @@
+// gx_kernels.cu — hydro/MHD step kernels for sm_100a (FP64 stencils, SoA layout).
+// Compiled twice: -DGX_FLAVOUR_STRICT with -fmad=false (bit-comparison build) and
+// -DGX_FLAVOUR_FAST with -fmad=true.
+//
+// Reference passes covered (file:line in the reference tree):
+//   k_calcprim  : calcprim/u2prim  src/hydro_core.f90:245-320, 46-129  (+ CFL candidates :644-675)
+//   k_flux      : hll?fluxes(choice) sweeps  src/hlld.f90:331-432 (hll/hllc/hlle identical)
+//   k_efield    : get_efield  src/flux_cd_module.f90:245-273
+//   k_update    : step + flux_cd_update + source  src/hydro_solver.f90:77-127,
+//                 src/flux_cd_module.f90:285-323, src/sources.f90:124-220
+//   k_viscous   : viscous_copy  src/hydro_solver.f90:47-65
+#include "gx_kernels.cuh"
+
+#if defined(GX_FLAVOUR_STRICT)
+#define GX_NS strict_ns
+#elif defined(GX_FLAVOUR_FAST)
+#define GX_NS fast_ns
+#else
+#error "define GX_FLAVOUR_STRICT or GX_FLAVOUR_FAST"
+#endif
+
+namespace gx {
+namespace GX_NS {
+
+using gxp::Phys;
+
+// ---------------------------------------------------------------------------
+// block-wide min of positive doubles -> one atomicMin on the ordered bit pattern
+__device__ __forceinline__ void block_atomic_min(double v, unsigned long long* dst) {
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __shared__ double smin[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) smin[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    v = lane < nw ? smin[lane] : 1.e30;
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) atomicMin(dst, (unsigned long long)__double_as_longlong(v));   // v > 0: bit order == value order
+  }
+}
+
+// ---------------------------------------------------------------------------
+template <bool MHD>
+__global__ void __launch_bounds__(128) k_calcprim(const StepArgs A, const double* __restrict__ U, double* __restrict__ W,
+                                                  double* __restrict__ Temp, unsigned long long* dtmin_bits, int want_cfl) {
+  const Grid& g = A.g;
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) - 1;   // Fortran i = -1 .. nx+2
+  const int j = (int)blockIdx.y - 1, k = (int)blockIdx.z - 1;
+  double dtp = 1.e30;
+  if (i <= g.nx + 2) {
+    const long long c = g.idx(i, j, k);
+    double u[8], w[8], T;
+#pragma unroll
+    for (int q = 0; q < (MHD ? 8 : 5); ++q) u[q] = U[q * g.vs + c];
+    const double pas0 = g.npas > 0 ? U[(long long)g.neqdyn * g.vs + c] : 0.0;
+    gxp::u2prim<MHD>(A.phys, u, w, pas0, T);
+#pragma unroll
+    for (int q = 0; q < (MHD ? 8 : 5); ++q) W[q * g.vs + c] = w[q];
+    for (int q = g.neqdyn; q < g.neq; ++q) W[q * g.vs + c] = U[q * g.vs + c];
+    if (Temp) Temp[c] = T;
+    if (want_cfl && i >= 1 && i <= g.nx && j >= 1 && j <= g.ny && k >= 1 && k <= g.nz) {
+      if (MHD) {
+        double cx, cy, cz;
+        gxp::cfast3(A.phys, w[4], w[0], w[5], w[6], w[7], cx, cy, cz);
+        dtp = fmin(dtp, g.dx / (fabs(w[1]) + cx));
+        dtp = fmin(dtp, g.dy / (fabs(w[2]) + cy));
+        dtp = fmin(dtp, g.dz / (fabs(w[3]) + cz));
+      } else {
+        double cs = gxp::csound(A.phys, w[4], w[0]);
+        dtp = fmin(dtp, g.dx / (fabs(w[1]) + cs));
+        dtp = fmin(dtp, g.dy / (fabs(w[2]) + cs));
+        dtp = fmin(dtp, g.dz / (fabs(w[3]) + cs));
+      }
+    }
+  }
+  if (want_cfl) block_atomic_min(dtp, dtmin_bits);
+}
+
+// ---------------------------------------------------------------------------
+// storage component of rotated slot c for sweep direction D (swapy / swapz as an index map)
+template <int D> __device__ __forceinline__ constexpr int comp(int c) {
+  return (c == 1) ? 1 + D : (c == 1 + D) ? 1 : (c == 5) ? 5 + D : (c == 5 + D) ? 5 : c;
+}
+
+// One thread = one interface (upper face of cell i,j,k in direction D).
+// Faces the update never reads are skipped.
+template <int SOLVER, int LIM, int ORDER, int D>
+__global__ void __launch_bounds__(128) k_flux(const StepArgs A, const double* __restrict__ W, double* __restrict__ F, int* errflag) {
+  constexpr bool MHD = (SOLVER == GX_SOLVER_HLLE || SOLVER == GX_SOLVER_HLLD);
+  constexpr int NQ = MHD ? 8 : 5;
+  const Grid& g = A.g;
+  // face index ranges: normal index 0..n, transverse 1..n
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) + (D == 0 ? 0 : 1);
+  const int j = (int)blockIdx.y + (D == 1 ? 0 : 1);
+  const int k = (int)blockIdx.z + (D == 2 ? 0 : 1);
+  if (i > g.nx) return;
+  const long long st = (D == 0) ? 1 : (D == 1) ? (long long)g.px : (long long)g.px * g.py;
+  const long long c = g.idx(i, j, k);
+  double wl[8], wr[8], ff[8];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const double* Wq = W + (long long)comp<D>(q) * g.vs + c;
+    double pl = Wq[0], pr = Wq[st];
+    if (ORDER == 2) gxp::reconstruct<LIM>(Wq[-st], pl, pr, Wq[2 * st]);
+    wl[q] = pl; wr[q] = pr;
+  }
+  gxp::PasInfo I;
+  int err = gxp::riemann<SOLVER>(A.phys, wl, wr, ff, I);
+  if (err) atomicOr(errflag, 1);
+  double* Fd = F + (long long)D * g.neq * g.vs + c;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) Fd[(long long)comp<D>(q) * g.vs] = ff[q];
+  for (int q = g.neqdyn; q < g.neq; ++q) {           // passive scalars (limited like every primitive)
+    const double* Wq = W + (long long)q * g.vs + c;
+    double pl = Wq[0], pr = Wq[st];
+    if (ORDER == 2) gxp::reconstruct<LIM>(Wq[-st], pl, pr, Wq[2 * st]);
+    Fd[(long long)q * g.vs] = gxp::passive_flux(I, pl, pr);
+  }
+}
+
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_efield(const StepArgs A, const double* __restrict__ F, double* __restrict__ E) {
+  const Grid& g = A.g;
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) + 1, j = (int)blockIdx.y + 1, k = (int)blockIdx.z + 1;
+  if (i > g.nx) return;
+  const long long c = g.idx(i, j, k), sy = g.px, sz = (long long)g.px * g.py, vs = g.vs;
+  const double* f = F;
+  const double* gg = F + (long long)g.neq * vs;
+  const double* h = F + 2LL * g.neq * vs;
+  // e(1) = 1/4(-g8(j-1) - g8(j) + h7(k-1) + h7(k)) etc.  (components are 0-based here: B = 5,6,7)
+  E[0 * vs + c] = 0.25 * (-gg[7 * vs + c - sy] - gg[7 * vs + c] + h[6 * vs + c - sz] + h[6 * vs + c]);
+  E[1 * vs + c] = 0.25 * (+f[7 * vs + c - 1] + f[7 * vs + c] - h[5 * vs + c - sz] - h[5 * vs + c]);
+  E[2 * vs + c] = 0.25 * (-f[6 * vs + c - 1] - f[6 * vs + c] + gg[5 * vs + c - sy] + gg[5 * vs + c]);
+}
+
+// ---------------------------------------------------------------------------
+template <bool FLUXCD>
+__global__ void __launch_bounds__(128) k_update(const StepArgs A, double dt, const double* __restrict__ U, const double* __restrict__ F,
+                                                const double* __restrict__ E, const double* __restrict__ W, double* __restrict__ dst) {
+  const Grid& g = A.g;
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) + 1, j = (int)blockIdx.y + 1, k = (int)blockIdx.z + 1;
+  if (i > g.nx) return;
+  const long long c = g.idx(i, j, k), sy = g.px, sz = (long long)g.px * g.py, vs = g.vs;
+  const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
+  const double* f = F;
+  const double* gg = F + (long long)g.neq * vs;
+  const double* h = F + 2LL * g.neq * vs;
+  const bool src = A.eight_wave || (A.user_src && A.grav.n > 0);
+  double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (src) {
+    // source(i,j,k,primit(:,i,j,k),s): src/sources.f90:190-220
+    double pp[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) pp[q] = (q < g.neqdyn) ? W[q * vs + c] : 0.0;
+    if (A.user_src) {
+      const double xc = ((double)(i + g.cx * g.nx - g.nxtot / 2) - 0.5) * g.dx;
+      const double yc = ((double)(j + g.cy * g.ny - g.nytot / 2) - 0.5) * g.dy;
+      const double zc = ((double)(k + g.cz * g.nz - g.nztot / 2) - 0.5) * g.dz;
+      for (int l = 0; l < A.grav.n; ++l) {
+        const double x = xc - A.grav.x[l], y = yc - A.grav.y[l], z = zc - A.grav.z[l];
+        const double rad2 = x * x + y * y + z * z;
+        const double r15 = pow(rad2, 1.5);
+        s[1] = s[1] - pp[0] * A.grav.gm[l] * x / r15;
+        s[2] = s[2] - pp[0] * A.grav.gm[l] * y / r15;
+        s[3] = s[3] - pp[0] * A.grav.gm[l] * z / r15;
+        s[4] = s[4] - pp[0] * A.grav.gm[l] * (pp[1] * x + pp[2] * y + pp[3] * z) / r15;
+      }
+    }
+    if (A.eight_wave && g.neqdyn == 8) {
+      const double d = (W[5 * vs + c + 1] - W[5 * vs + c - 1]) / (2. * g.dx)
+                     + (W[6 * vs + c + sy] - W[6 * vs + c - sy]) / (2. * g.dy)
+                     + (W[7 * vs + c + sz] - W[7 * vs + c - sz]) / (2. * g.dz);
+      s[1] = s[1] - d * pp[5];
+      s[2] = s[2] - d * pp[6];
+      s[3] = s[3] - d * pp[7];
+      s[4] = s[4] - d * (pp[1] * pp[5] + pp[2] * pp[6] + pp[3] * pp[7]);
+      s[5] = s[5] - d * pp[1];
+      s[6] = s[6] - d * pp[2];
+      s[7] = s[7] - d * pp[3];
+    }
+  }
+  for (int q = 0; q < g.neq; ++q) {
+    const long long o = q * vs + c;
+    double v;
+    if (FLUXCD && q >= 5 && q < 8) {
+      // evolution of B with flux-CD: src/flux_cd_module.f90:311-321
+      if (q == 5) v = U[o] - 0.5 * dtdy * (E[2 * vs + c + sy] - E[2 * vs + c - sy]) + 0.5 * dtdz * (E[1 * vs + c + sz] - E[1 * vs + c - sz]);
+      else if (q == 6) v = U[o] + 0.5 * dtdx * (E[2 * vs + c + 1] - E[2 * vs + c - 1]) - 0.5 * dtdz * (E[0 * vs + c + sz] - E[0 * vs + c - sz]);
+      else v = U[o] - 0.5 * dtdx * (E[1 * vs + c + 1] - E[1 * vs + c - 1]) + 0.5 * dtdy * (E[0 * vs + c + sy] - E[0 * vs + c - sy]);
+    } else {
+      v = U[o] - dtdx * (f[o] - f[o - 1]) - dtdy * (gg[o] - gg[o - sy]) - dtdz * (h[o] - h[o - sz]);
+    }
+    if (src) v = v + dt * (q < 8 ? s[q] : 0.0);
+    dst[o] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_viscous(const StepArgs A, double eta, const double* __restrict__ UP, double* __restrict__ U) {
+  const Grid& g = A.g;
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) + 1, j = (int)blockIdx.y + 1, k = (int)blockIdx.z + 1;
+  if (i > g.nx) return;
+  const long long c = g.idx(i, j, k), sy = g.px, sz = (long long)g.px * g.py;
+  for (int q = 0; q < g.neq; ++q) {
+    const double* p = UP + q * g.vs + c;
+    U[q * g.vs + c] = p[0] + eta * (p[1] + p[-1] + p[sy] + p[-sy] + p[sz] + p[-sz] - 6. * p[0]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+static inline dim3 grid_for(int nxr, int nyr, int nzr, int bx) { return dim3((unsigned)((nxr + bx - 1) / bx), (unsigned)nyr, (unsigned)nzr); }
+
+static void l_calcprim(const StepArgs& A, const double* U, double* W, double* Temp, unsigned long long* dtmin_bits, int want_cfl, cudaStream_t s) {
+  const Grid& g = A.g;
+  dim3 grid = grid_for(g.nx + 4, g.ny + 4, g.nz + 4, 128);
+  if (A.phys.neqdyn == 8) k_calcprim<true><<<grid, 128, 0, s>>>(A, U, W, Temp, dtmin_bits, want_cfl);
+  else k_calcprim<false><<<grid, 128, 0, s>>>(A, U, W, Temp, dtmin_bits, want_cfl);
+}
+
+template <int SOLVER, int LIM, int ORDER>
+static void l_flux3(const StepArgs& A, const double* W, double* F, int* errflag, cudaStream_t s) {
+  const Grid& g = A.g;
+  k_flux<SOLVER, LIM, ORDER, 0><<<grid_for(g.nx + 1, g.ny, g.nz, 128), 128, 0, s>>>(A, W, F, errflag);
+  k_flux<SOLVER, LIM, ORDER, 1><<<grid_for(g.nx, g.ny + 1, g.nz, 128), 128, 0, s>>>(A, W, F, errflag);
+  k_flux<SOLVER, LIM, ORDER, 2><<<grid_for(g.nx, g.ny, g.nz + 1, 128), 128, 0, s>>>(A, W, F, errflag);
+}
+
+template <int SOLVER>
+static int l_flux_solver(const StepArgs& A, int order, const double* W, double* F, int* errflag, cudaStream_t s) {
+  if (order == 1) { l_flux3<SOLVER, GX_LIMITER_NO_AVERAGE, 1>(A, W, F, errflag, s); return 0; }
+  switch (A.limiter) {
+    case GX_LIMITER_NO_AVERAGE: l_flux3<SOLVER, GX_LIMITER_NO_AVERAGE, 2>(A, W, F, errflag, s); return 0;
+    case GX_LIMITER_NO_LIMIT:   l_flux3<SOLVER, GX_LIMITER_NO_LIMIT, 2>(A, W, F, errflag, s); return 0;
+    case GX_LIMITER_MINMOD:     l_flux3<SOLVER, GX_LIMITER_MINMOD, 2>(A, W, F, errflag, s); return 0;
+    case GX_LIMITER_VAN_LEER:   l_flux3<SOLVER, GX_LIMITER_VAN_LEER, 2>(A, W, F, errflag, s); return 0;
+    case GX_LIMITER_VAN_ALBADA: l_flux3<SOLVER, GX_LIMITER_VAN_ALBADA, 2>(A, W, F, errflag, s); return 0;
+    case GX_LIMITER_UMIST:      l_flux3<SOLVER, GX_LIMITER_UMIST, 2>(A, W, F, errflag, s); return 0;
+    case GX_LIMITER_WOODWARD:   l_flux3<SOLVER, GX_LIMITER_WOODWARD, 2>(A, W, F, errflag, s); return 0;
+    case GX_LIMITER_SUPERBEE:   l_flux3<SOLVER, GX_LIMITER_SUPERBEE, 2>(A, W, F, errflag, s); return 0;
+  }
+  return GX_EINVAL;
+}
+
+static int l_fluxes(const StepArgs& A, int order, const double* W, double* F, int* errflag, cudaStream_t s) {
+  switch (A.solver) {
+    case GX_SOLVER_HLL:  return l_flux_solver<GX_SOLVER_HLL>(A, order, W, F, errflag, s);
+    case GX_SOLVER_HLLC: return l_flux_solver<GX_SOLVER_HLLC>(A, order, W, F, errflag, s);
+    case GX_SOLVER_HLLE: return l_flux_solver<GX_SOLVER_HLLE>(A, order, W, F, errflag, s);
+    case GX_SOLVER_HLLD: return l_flux_solver<GX_SOLVER_HLLD>(A, order, W, F, errflag, s);
+  }
+  return GX_EUNSUPPORTED;
+}
+
+static void l_efield(const StepArgs& A, const double* F, double* E, cudaStream_t s) {
+  const Grid& g = A.g;
+  k_efield<<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(A, F, E);
+}
+
+static void l_update(const StepArgs& A, double dt, const double* U, const double* F, const double* E, const double* W, double* dst, cudaStream_t s) {
+  const Grid& g = A.g;
+  dim3 grid = grid_for(g.nx, g.ny, g.nz, 128);
+  if (A.flux_cd) k_update<true><<<grid, 128, 0, s>>>(A, dt, U, F, E, W, dst);
+  else k_update<false><<<grid, 128, 0, s>>>(A, dt, U, F, E, W, dst);
+}
+
+static void l_viscous(const StepArgs& A, double eta, const double* UP, double* U, cudaStream_t s) {
+  const Grid& g = A.g;
+  k_viscous<<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(A, eta, UP, U);
+}
+
+static const KernelTable table = {l_calcprim, l_fluxes, l_efield, l_update, l_viscous};
+
+}  // namespace GX_NS
+
+#if defined(GX_FLAVOUR_STRICT)
+const KernelTable* kernels_strict() { return &strict_ns::table; }
+#else
+const KernelTable* kernels_fast() { return &fast_ns::table; }
+#endif
+
+}  // namespace gx

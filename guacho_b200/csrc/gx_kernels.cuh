@@ -1,0 +1,59 @@
+// gx_kernels.cuh — device layout + kernel declarations shared by the API layer and
+// the two kernel builds (strict: -fmad=false, fast: -fmad=true).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "gx_physics.cuh"
+
+namespace gx {
+
+// Device layout: SoA, x fastest.  Variable v of cell (i,j,k) [Fortran indices,
+// i = 1-ng .. nx+ng] lives at  v*vs + ((k+1)*py + (j+1))*px + (i + xo).
+// xo = 15 puts the first physical cell (i=1) on a 128-byte boundary of every row
+// (px is a multiple of 16 doubles, cudaMalloc bases are 256-byte aligned), so a warp
+// reading 32 consecutive physical cells touches exactly two 128-byte lines.
+struct Grid {
+  int nx, ny, nz;          // physical cells of this block
+  int px, py, pz;          // padded extents (px: row pitch in doubles)
+  int xo;                  // x offset of Fortran index 0
+  long long vs;            // variable stride = px*py*pz
+  int neq, neqdyn, npas;
+  int cx, cy, cz;          // block coords (for positions in source terms)
+  int nxtot, nytot, nztot;
+  double dx, dy, dz;
+  __host__ __device__ __forceinline__ long long idx(int i, int j, int k) const {
+    return ((long long)(k + 1) * py + (j + 1)) * px + (i + xo);
+  }
+};
+
+struct GravityPoints {     // get_user_source_terms functor (EXO/user_mod.f90:158-206)
+  int n;
+  double gm[4], x[4], y[4], z[4];
+};
+
+struct StepArgs {
+  Grid g;
+  gxp::Phys phys;
+  int solver, limiter;
+  int flux_cd, eight_wave, user_src;
+  GravityPoints grav;
+};
+
+// classes for the per-kernel timing table (gx_kernel_time_ms)
+enum { KC_FLUX = 0, KC_UPDATE = 1, KC_EFIELD = 2, KC_PRIM = 3, KC_BC = 4, KC_XPOSE = 5, KC_VISC = 6, KC_COUNT = 7 };
+
+// One set of launchers per build flavour.
+struct KernelTable {
+  // primitives (+Temp, + CFL min into *dtmin_bits when want_cfl) over the whole padded array
+  void (*calcprim)(const StepArgs&, const double* U, double* W, double* Temp, unsigned long long* dtmin_bits, int want_cfl, cudaStream_t);
+  // face fluxes, order 1|2, all three directions (3 launches)
+  int (*fluxes)(const StepArgs&, int order, const double* W, double* F, int* errflag, cudaStream_t);
+  void (*efield)(const StepArgs&, const double* F, double* E, cudaStream_t);
+  // dst = U - dt*div(F) [flux-CD for B] [+ dt*S(W)]
+  void (*update)(const StepArgs&, double dt, const double* U, const double* F, const double* E, const double* W, double* dst, cudaStream_t);
+  void (*viscous)(const StepArgs&, double eta, const double* UP, double* U, cudaStream_t);
+};
+const KernelTable* kernels_strict();
+const KernelTable* kernels_fast();
+
+}  // namespace gx

@@ -1,0 +1,365 @@
+// gx_physics.cuh — per-cell / per-interface device functions of the hydro/MHD step.
+//
+// Register-resident, branch-uniform-where-possible formulations of the reference's
+// cell-level routines.  Slot convention for a state rotated into sweep direction d:
+//   w[0]=rho  w[1]=v_n  w[2]=v_t1  w[3]=v_t2  w[4]=p  w[5]=B_n  w[6]=B_t1  w[7]=B_t2
+// which is what swapy/swapz (src/hydro_core.f90:485-534) produce; the rotation is done
+// by the loader through a component permutation, never by moving data.
+// Operation ORDER follows the reference expressions so that a -fmad=false build is
+// bit-comparable with the no-FMA x86 reference build.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include "../../include/guacho_gx.h"
+
+namespace gxp {
+
+struct Phys {            // the scalar `parameter`s the cell routines read
+  double cv, gamma, Tempsc;
+  int eos;               // GX_EOS_*
+  int neqdyn, npas;      // neq = neqdyn + npas
+};
+
+__device__ __forceinline__ double sign1(double x) { return copysign(1.0, x); }   // Fortran sign(1.,x)
+
+// ---- u2prim: src/hydro_core.f90:46-129 (dynamic variables only; passives are copies) ----
+// `pas0` is the first passive (needed by EOS_H_RATE only).
+template <bool MHD>
+__device__ __forceinline__ void u2prim(const Phys& P, const double (&u)[8], double (&w)[8], double pas0, double& T) {
+  double r = fmax(u[0], 1e-15);
+  w[0] = r;
+  w[1] = u[1] / r;
+  w[2] = u[2] / r;
+  w[3] = u[3] / r;
+  double ek = 0.5 * r * (w[1] * w[1] + w[2] * w[2] + w[3] * w[3]);
+  double p;
+  if (MHD) p = (u[4] - ek - 0.5 * (u[5] * u[5] + u[6] * u[6] + u[7] * u[7])) / P.cv;
+  else p = (u[4] - ek) / P.cv;
+  p = fmax(p, 1e-16);
+  if (MHD) { w[5] = u[5]; w[6] = u[6]; w[7] = u[7]; }
+  T = 0.0;
+  if (P.eos == GX_EOS_ADIABATIC) {
+    T = (p / r) * P.Tempsc;
+  } else if (P.eos == GX_EOS_SINGLE_SPECIE) {
+    double rr = fmax(r, 1e-15);
+    T = fmax(1.0, (p / rr) * P.Tempsc);
+    p = rr * T / P.Tempsc;
+  } else if (P.eos == GX_EOS_H_RATE && P.npas > 0) {
+    double dentot = fmax(2.0 * r - pas0, 1e-15);
+    T = fmax(1.0, (p / dentot) * P.Tempsc);
+    p = dentot * T / P.Tempsc;
+  }
+  w[4] = p;
+}
+
+// ---- wave speeds: src/hydro_core.f90:544-604 ----
+__device__ __forceinline__ double csound(const Phys& P, double p, double d) { return sqrt(P.gamma * p / d); }
+
+__device__ __forceinline__ double cfastX(const Phys& P, const double (&w)[8]) {
+  double b2 = w[5] * w[5] + w[6] * w[6] + w[7] * w[7];
+  double cs2va2 = (P.gamma * w[4] + b2) / w[0];
+  return sqrt(0.5 * (cs2va2 + sqrt(cs2va2 * cs2va2 - 4. * P.gamma * w[4] * (w[5] * w[5]) / w[0] / w[0])));
+}
+
+// CFL form (src/hydro_core.f90:568-581): fast speed along each axis
+__device__ __forceinline__ void cfast3(const Phys& P, double p, double d, double bx, double by, double bz,
+                                       double& cx, double& cy, double& cz) {
+  double b2 = bx * bx + by * by + bz * bz;
+  double gpb = P.gamma * p + b2;
+  double gp4 = 4. * P.gamma * p;
+  cx = sqrt(0.5 * (gpb + sqrt(gpb * gpb - gp4 * bx * bx)) / d);
+  cy = sqrt(0.5 * (gpb + sqrt(gpb * gpb - gp4 * by * by)) / d);
+  cz = sqrt(0.5 * (gpb + sqrt(gpb * gpb - gp4 * bz * bz)) / d);
+}
+
+// ---- prim2f / prim2u: src/hydro_core.f90:331-476 (non-split branches) ----
+template <bool MHD>
+__device__ __forceinline__ void prim2f(const Phys& P, const double (&w)[8], double (&ff)[8]) {
+  double v2 = w[1] * w[1] + w[2] * w[2] + w[3] * w[3];
+  if (MHD) {
+    double b2 = w[5] * w[5] + w[6] * w[6] + w[7] * w[7];
+    double etot = 0.5 * (w[0] * v2 + w[5] * w[5] + w[6] * w[6] + w[7] * w[7]) + P.cv * w[4];
+    ff[0] = w[0] * w[1];
+    ff[1] = w[0] * w[1] * w[1] + w[4] + 0.5 * (w[6] * w[6] + w[7] * w[7] - w[5] * w[5]);
+    ff[2] = w[0] * w[1] * w[2] - w[5] * w[6];
+    ff[3] = w[0] * w[1] * w[3] - w[5] * w[7];
+    ff[4] = w[1] * (etot + w[4] + 0.5 * b2) - w[5] * (w[1] * w[5] + w[2] * w[6] + w[3] * w[7]);
+    ff[5] = 0.0;
+    ff[6] = w[1] * w[6] - w[5] * w[2];
+    ff[7] = w[1] * w[7] - w[5] * w[3];
+  } else {
+    double etot = 0.5 * w[0] * v2 + P.cv * w[4];
+    ff[0] = w[0] * w[1];
+    ff[1] = w[0] * w[1] * w[1] + w[4];
+    ff[2] = w[0] * w[1] * w[2];
+    ff[3] = w[0] * w[1] * w[3];
+    ff[4] = w[1] * (etot + w[4]);
+  }
+}
+
+template <bool MHD>
+__device__ __forceinline__ void prim2u(const Phys& P, const double (&w)[8], double (&uu)[8]) {
+  uu[0] = w[0];
+  uu[1] = w[0] * w[1];
+  uu[2] = w[0] * w[2];
+  uu[3] = w[0] * w[3];
+  uu[4] = 0.5 * w[0] * (w[1] * w[1] + w[2] * w[2] + w[3] * w[3]) + P.cv * w[4];
+  if (MHD) {
+    uu[4] = uu[4] + 0.5 * (w[5] * w[5] + w[6] * w[6] + w[7] * w[7]);
+    uu[5] = w[5]; uu[6] = w[6]; uu[7] = w[7];
+  }
+}
+
+// ---- slope limiters: src/hydro_core.f90:735-796 ----
+template <int LIM>
+__device__ __forceinline__ double average(double a, double b) {
+  if (LIM == GX_LIMITER_NO_AVERAGE) return 0.;
+  if (LIM == GX_LIMITER_NO_LIMIT) return 0.5 * (a + b);
+  if (LIM == GX_LIMITER_MINMOD) {
+    double s = sign1(a);
+    return s * fmax(0., fmin(fabs(a), s * b));
+  }
+  if (LIM == GX_LIMITER_VAN_LEER) {
+    if (a * b <= 0.) return 0.;
+    return a * b * (a + b) / (a * a + b * b);
+  }
+  if (LIM == GX_LIMITER_VAN_ALBADA) {
+    const double delta = 1.e-7;
+    return (a * (b * b + delta) + b * (a * a + delta)) / (a * a + b * b + delta);
+  }
+  if (LIM == GX_LIMITER_UMIST) {
+    double s = sign1(a);
+    double c = 0.25 * a + 0.75 * b;
+    double d = 0.75 * a + 0.25 * b;
+    double m = fmin(fmin(2. * fabs(a), 2. * s * b), fmin(s * c, s * d));
+    return s * fmax(0., m);
+  }
+  if (LIM == GX_LIMITER_WOODWARD) {
+    double s = sign1(a);
+    double c = 0.5 * (a + b);
+    double m = fmin(fmin(2. * fabs(a), 2. * s * b), s * c);
+    return s * fmax(0., m);
+  }
+  if (LIM == GX_LIMITER_SUPERBEE) {
+    double s = sign1(b);
+    double av1 = fmin(2. * fabs(b), s * a);
+    double av2 = fmin(fabs(b), 2. * s * a);
+    return s * fmax(0., fmax(av1, av2));
+  }
+  return 0.;
+}
+
+// reconstruct one variable at the interface between pl and pr (src/hydro_core.f90:723-731)
+template <int LIM>
+__device__ __forceinline__ void reconstruct(double pll, double& pl, double& pr, double prr) {
+  double dl = pl - pll;
+  double dm = pr - pl;
+  double dr = prr - pr;
+  double al = average<LIM>(dl, dm);
+  double ar = average<LIM>(dm, dr);
+  pl = pl + al * 0.5;
+  pr = pr - ar * 0.5;
+}
+
+// ---- passive-scalar flux bookkeeping ----
+// Every solver advects passives with one of a few closed forms; the solver records
+// which one applied and the scalars it needs, the sweep then applies it per passive.
+enum { PAS_UPL = 0, PAS_UPR = 1, PAS_HLL = 2, PAS_HLLC_L = 3, PAS_HLLC_R = 4, PAS_HLLD_L = 5, PAS_HLLD_R = 6 };
+struct PasInfo {
+  int mode;
+  double ul, ur, sl, sr, a, b, c;   // meaning depends on mode
+};
+__device__ __forceinline__ double passive_flux(const PasInfo& I, double ql, double qr) {
+  switch (I.mode) {
+    case PAS_UPL: return ql * I.ul;                                       // prim2f(L): hydro_core.f90:472
+    case PAS_UPR: return qr * I.ur;
+    case PAS_HLL: return (I.sr * (ql * I.ul) - I.sl * (qr * I.ur) + I.sl * I.sr * (qr - ql)) / (I.sr - I.sl);   // hll.f90:76
+    case PAS_HLLC_L: return ql * I.ul + I.sl * (I.a * ql / I.b - ql);     // hllc.f90:94-101: a=rhost, b=rhoL
+    case PAS_HLLC_R: return qr * I.ur + I.sr * (I.a * qr / I.b - qr);
+    case PAS_HLLD_L: return I.a * ql * I.b / I.c;                         // hlld.f90:151: a=sM, b=slmul, c=slmsM
+    case PAS_HLLD_R: return I.a * qr * I.b / I.c;
+  }
+  return 0.;
+}
+
+// ---- HLL (hydro speeds) / HLLE (fast speeds): src/hll.f90:47-82, src/hlle.f90:48-83 ----
+template <bool MHD, bool FAST>
+__device__ __forceinline__ int riemann_hll(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
+  double csl, csr;
+  if (FAST) { csl = cfastX(P, wl); csr = cfastX(P, wr); }
+  else { csl = csound(P, wl[4], wl[0]); csr = csound(P, wr[4], wr[0]); }
+  double sr = fmax(wl[1] + csl, wr[1] + csr);
+  double sl = fmin(wl[1] - csl, wr[1] - csr);
+  I.ul = wl[1]; I.ur = wr[1]; I.sl = sl; I.sr = sr;
+  if (sl > 0) { prim2f<MHD>(P, wl, ff); I.mode = PAS_UPL; return 0; }
+  if (sr < 0) { prim2f<MHD>(P, wr, ff); I.mode = PAS_UPR; return 0; }
+  double fL[8], fR[8], uL[8], uR[8];
+  prim2f<MHD>(P, wl, fL); prim2f<MHD>(P, wr, fR);
+  prim2u<MHD>(P, wl, uL); prim2u<MHD>(P, wr, uR);
+  const int n = MHD ? 8 : 5;
+#pragma unroll
+  for (int q = 0; q < n; ++q) ff[q] = (sr * fL[q] - sl * fR[q] + sl * sr * (uR[q] - uL[q])) / (sr - sl);
+  I.mode = PAS_HLL;
+  return 0;
+}
+
+// ---- HLLC: src/hllc.f90:44-140 (hydro) ----
+__device__ __forceinline__ int riemann_hllc(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
+  double csl = csound(P, wl[4], wl[0]);
+  double csr = csound(P, wr[4], wr[0]);
+  double sr = fmax(wl[1] + csl, wr[1] + csr);
+  double sl = fmin(wl[1] - csl, wr[1] - csr);
+  I.ul = wl[1]; I.ur = wr[1]; I.sl = sl; I.sr = sr;
+  if (sl > 0) { prim2f<false>(P, wl, ff); I.mode = PAS_UPL; return 0; }
+  if (sr < 0) { prim2f<false>(P, wr, ff); I.mode = PAS_UPR; return 0; }
+  double slmul = sl - wl[1];
+  double srmur = sr - wr[1];
+  double rholul = wl[0] * wl[1];
+  double rhorur = wr[0] * wr[1];
+  double sst = (srmur * rhorur - slmul * rholul - wr[4] + wl[4]) / (srmur * wr[0] - slmul * wl[0]);
+  double uu[8], uuk[8];
+  if (sst >= 0.) {
+    double rhost = wl[0] * (slmul) / (sl - sst);
+    double ek = 0.5 * wl[0] * (wl[1] * wl[1] + wl[2] * wl[2] + wl[3] * wl[3]) + P.cv * wl[4];
+    uuk[0] = rhost;
+    uuk[1] = rhost * sst;
+    uuk[2] = rhost * wl[2];
+    uuk[3] = rhost * wl[3];
+    uuk[4] = rhost * (ek / wl[0] + (sst - wl[1]) * (sst + wl[4] / (wl[0] * slmul)));
+    prim2f<false>(P, wl, ff);
+    prim2u<false>(P, wl, uu);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) ff[q] = ff[q] + sl * (uuk[q] - uu[q]);
+    I.mode = PAS_HLLC_L; I.a = rhost; I.b = wl[0];
+    return 0;
+  }
+  if (sst <= 0.) {
+    double rhost = wr[0] * (srmur) / (sr - sst);
+    double ek = 0.5 * wr[0] * (wr[1] * wr[1] + wr[2] * wr[2] + wr[3] * wr[3]) + P.cv * wr[4];
+    uuk[0] = rhost;
+    uuk[1] = rhost * sst;
+    uuk[2] = rhost * wr[2];
+    uuk[3] = rhost * wr[3];
+    uuk[4] = rhost * (ek / wr[0] + (sst - wr[1]) * (sst + wr[4] / (wr[0] * srmur)));
+    prim2f<false>(P, wr, ff);
+    prim2u<false>(P, wr, uu);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) ff[q] = ff[q] + sr * (uuk[q] - uu[q]);
+    I.mode = PAS_HLLC_R; I.a = rhost; I.b = wr[0];
+    return 0;
+  }
+  return 1;   // NaN: the reference prints 'Error in hllc' and stops (hllc.f90:135-138)
+}
+
+// ---- HLLD (Miyoshi & Kusano 2005 five-wave): src/hlld.f90:48-319 ----
+// One-sided star state (used for both sides with the roles of L/R exchanged).
+struct Star { double v, w, by, bz; };
+__device__ __forceinline__ Star hlld_star(const double (&q)[8], double bx, double smu /*S_K - u_K*/, double sms /*S_K - S_M*/, double sMmu /*S_M - u_K*/) {
+  Star s;
+  double den = q[0] * smu * sms - bx * bx;
+  if (den == 0) {                      // hlld.f90:119-126 degenerate guard
+    s.v = q[2]; s.w = q[3]; s.by = 0.; s.bz = 0.;
+  } else {
+    s.v = q[2] - bx * q[6] * sMmu / den;
+    s.w = q[3] - bx * q[7] * sMmu / den;
+    double num = q[0] * (smu * smu) - bx * bx;
+    s.by = q[6] * num / den;
+    s.bz = q[7] * num / den;
+  }
+  return s;
+}
+// total energy of side K with the interface-averaged Bx (hlld.f90:113-114)
+__device__ __forceinline__ double hlld_energy(const Phys& P, const double (&q)[8], double bx) {
+  return 0.5 * q[0] * (q[1] * q[1] + q[2] * q[2] + q[3] * q[3]) + P.cv * q[4] + 0.5 * (bx * bx + q[6] * q[6] + q[7] * q[7]);
+}
+
+__device__ __forceinline__ int riemann_hlld(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
+  double csl = cfastX(P, wl);
+  double csr = cfastX(P, wr);
+  double sr = fmax(wl[1] + csl, wr[1] + csr);
+  double sl = fmin(wl[1] - csl, wr[1] - csr);
+  I.ul = wl[1]; I.ur = wr[1]; I.sl = sl; I.sr = sr;
+  if (sl > 0) { prim2f<true>(P, wl, ff); I.mode = PAS_UPL; return 0; }
+  if (sr < 0) { prim2f<true>(P, wr, ff); I.mode = PAS_UPR; return 0; }
+
+  double bx = 0.5 * (wl[5] + wr[5]);
+  double signBx = sign1(bx);
+  double pTL = wl[4] + 0.5 * (bx * bx + wl[6] * wl[6] + wl[7] * wl[7]);
+  double pTR = wr[4] + 0.5 * (bx * bx + wr[6] * wr[6] + wr[7] * wr[7]);
+  double slmul = sl - wl[1];
+  double srmur = sr - wr[1];
+  double rholul = wl[0] * wl[1];
+  double rhorur = wr[0] * wr[1];
+  double den = srmur * wr[0] - slmul * wl[0];
+  double sM = (srmur * rhorur - slmul * rholul - pTR + pTL) / den;
+  double srmsM = sr - sM;
+  double slmsM = sl - sM;
+  double rhostl = wl[0] * slmul / slmsM;
+  double rhostr = wr[0] * srmur / srmsM;
+  double sql = sqrt(rhostl), sqr = sqrt(rhostr);
+  double sstl = sM - fabs(bx) / sql;
+  double sstr = sM + fabs(bx) / sqr;
+  double pst = (srmur * wr[0] * pTL - slmul * wl[0] * pTR + wl[0] * wr[0] * srmur * slmul * (wr[1] - wl[1])) / den;
+
+  // Which side supplies the outer state: L for UL*, UL**; R for UR*, UR**.
+  // Region order as in the reference: sstl>=0, sstr<=0, sM>=0, sM<=0.
+  const bool starL = (sstl >= 0), starR = !starL && (sstr <= 0);
+  const bool dstar = !starL && !starR;
+  if (dstar && !(sM >= 0) && !(sM <= 0)) return 1;          // NaN: 'Error in HLLD routine' + stop
+  const bool left = starL || (dstar && sM >= 0);
+
+  Star SL, SR;
+  if (left || dstar) SL = hlld_star(wl, bx, slmul, slmsM, sM - wl[1]);
+  if (!left || dstar) SR = hlld_star(wr, bx, srmur, srmsM, sM - wr[1]);
+
+  double vs, ws, bys, bzs, vdb_ss = 0.;     // state used in the flux (star or double-star)
+  if (dstar) {
+    double dd = sql + sqr;
+    double sq2 = sqrt(rhostl * rhostr);
+    vs = (sql * SL.v + sqr * SR.v + (SR.by - SL.by) * signBx) / dd;
+    ws = (sql * SL.w + sqr * SR.w + (SR.bz - SL.bz) * signBx) / dd;
+    bys = (sql * SR.by + sqr * SL.by + sq2 * (SR.v - SL.v) * signBx) / dd;
+    bzs = (sql * SR.bz + sqr * SL.bz + sq2 * (SR.w - SL.w) * signBx) / dd;
+    vdb_ss = sM * bx + vs * bys + ws * bzs;
+  }
+
+  double rhost, es;
+  if (left) {
+    double el = hlld_energy(P, wl, bx);
+    double vdotb = wl[1] * bx + wl[2] * wl[6] + wl[3] * wl[7];
+    double vsdotbs = sM * bx + SL.v * SL.by + SL.w * SL.bz;
+    double estl = (slmul * el - pTL * wl[1] + pst * sM + bx * (vdotb - vsdotbs)) / slmsM;
+    rhost = rhostl;
+    if (dstar) { es = estl - sql * (vsdotbs - vdb_ss) * signBx; }
+    else { es = estl; vs = SL.v; ws = SL.w; bys = SL.by; bzs = SL.bz; vdb_ss = vsdotbs; }
+    I.mode = PAS_HLLD_L; I.a = sM; I.b = slmul; I.c = slmsM;
+  } else {
+    double er = hlld_energy(P, wr, bx);
+    double vdotb = wr[1] * bx + wr[2] * wr[6] + wr[3] * wr[7];
+    double vsdotbs = sM * bx + SR.v * SR.by + SR.w * SR.bz;
+    double estr = (srmur * er - pTR * wr[1] + pst * sM + bx * (vdotb - vsdotbs)) / srmsM;
+    rhost = rhostr;
+    if (dstar) { es = estr + sqr * (vsdotbs - vdb_ss) * signBx; }
+    else { es = estr; vs = SR.v; ws = SR.w; bys = SR.by; bzs = SR.bz; vdb_ss = vsdotbs; }
+    I.mode = PAS_HLLD_R; I.a = sM; I.b = srmur; I.c = srmsM;
+  }
+  ff[0] = rhost * sM;
+  ff[1] = rhost * (sM * sM) + pst - bx * bx;
+  ff[2] = rhost * sM * vs - bx * bys;
+  ff[3] = rhost * sM * ws - bx * bzs;
+  ff[4] = sM * (es + pst) - bx * (vdb_ss);
+  ff[5] = 0.;
+  ff[6] = bys * sM - bx * vs;
+  ff[7] = bzs * sM - bx * ws;
+  return 0;
+}
+
+template <int SOLVER>
+__device__ __forceinline__ int riemann(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
+  if (SOLVER == GX_SOLVER_HLL) return riemann_hll<false, false>(P, wl, wr, ff, I);
+  if (SOLVER == GX_SOLVER_HLLE) return riemann_hll<true, true>(P, wl, wr, ff, I);
+  if (SOLVER == GX_SOLVER_HLLC) return riemann_hllc(P, wl, wr, ff, I);
+  return riemann_hlld(P, wl, wr, ff, I);
+}
+
+}  // namespace gxp

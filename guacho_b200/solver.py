@@ -1,0 +1,225 @@
+"""Host-side mirror of the reference's driver for the hot path.
+
+:class:`Block` wraps one ``gx_solver`` (= one MPI rank / one GPU of the reference's
+Cartesian decomposition) and exposes the calls ``src/main.f90`` makes into the step:
+``initflow -> boundaryI -> calcprim`` (:meth:`set_state`), ``get_timestep``, ``tstep``,
+and "state on the host before write_output" (:meth:`get_state`).  :class:`Simulation`
+mirrors the time loop of ``src/main.f90:94-125``.
+
+Everything numerical happens inside libguacho_gx.so; this module only marshals
+numpy arrays in the reference layout ``(neq, nx+4, ny+4, nz+4)`` (Fortran order).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from . import lib as _lib
+from .config import Params
+from .lib import GxError, WindSphere, check, KERNEL_CLASSES
+
+
+def _dp(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Block:
+    """One block of the domain on one GPU (reference: one MPI rank)."""
+
+    def __init__(self, params: Params, coords: Sequence[int] = (0, 0, 0)):
+        params.validate()
+        self.p = params
+        self.coords = tuple(int(c) for c in coords)
+        self.L = _lib.load()
+        self._cfg = params.to_c(self.coords)
+        h = C.c_void_p()
+        check(self.L.gx_create(C.byref(self._cfg), C.byref(h)))
+        self.h = h
+        self._host_bc_ref = None
+
+    # -- lifetime --
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.L.gx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- shapes --
+    @property
+    def shape(self):
+        return self.p.block_shape()
+
+    @property
+    def rank(self) -> int:
+        """Row-major rank <-> coords map of the reference (py/guacho_utils.py:104-118)."""
+        cx, cy, cz = self.coords
+        return (cx * self.p.MPI_NBY + cy) * self.p.MPI_NBZ + cz
+
+    def empty_state(self) -> np.ndarray:
+        return np.zeros(self.shape, dtype=np.float64, order="F")
+
+    # -- calls main.f90 makes --
+    def set_state(self, u: np.ndarray) -> None:
+        """initflow -> boundaryI -> calcprim (main.f90:73-79)."""
+        if u.shape != self.shape:
+            raise ValueError(f"u has shape {u.shape}, expected {self.shape}")
+        a = np.asfortranarray(u, dtype=np.float64)
+        check(self.L.gx_set_state(self.h, _dp(a)))
+
+    def set_time(self, time: float) -> None:
+        check(self.L.gx_set_time(self.h, float(time)))
+
+    def get_timestep(self, current_iter: int, n_iter: int, current_time: float, tprint: float):
+        """get_timestep (hydro_core.f90:623-697) -> (dt, dump_flag)."""
+        dt = C.c_double(0.0)
+        dump = C.c_int32(0)
+        check(self.L.gx_get_timestep(self.h, current_iter, n_iter, current_time, tprint, C.byref(dt), C.byref(dump)))
+        return dt.value, bool(dump.value)
+
+    def tstep(self, dt_cfl: float) -> None:
+        """tstep (hydro_solver.f90:134-229)."""
+        check(self.L.gx_tstep(self.h, float(dt_cfl)))
+
+    def run(self, n_steps: int, time: float, it: int, n_iter_ramp: int = 10):
+        """n_steps iterations of main.f90's loop body, without output -> (time, iter, last_dt)."""
+        t = C.c_double(time)
+        i = C.c_int32(it)
+        last = C.c_double(0.0)
+        check(self.L.gx_run(self.h, n_steps, n_iter_ramp, C.byref(t), C.byref(i), C.byref(last)))
+        return t.value, i.value, last.value
+
+    def get_state(self, u: bool = True, primit: bool = False, temp: bool = False):
+        """State on the host in reference layout (before write_output, main.f90:85,112)."""
+        p = self.p
+        ua = self.empty_state() if u else None
+        pa = self.empty_state() if primit else None
+        ta = np.zeros((p.nx + 4, p.ny + 4, p.nz + 4), dtype=np.float64, order="F") if temp else None
+        check(self.L.gx_get_state(self.h, _dp(ua), _dp(pa), _dp(ta)))
+        out = [a for a in (ua, pa, ta) if a is not None]
+        return out[0] if len(out) == 1 else tuple(out)
+
+    def get_state_into(self, u: np.ndarray) -> None:
+        check(self.L.gx_get_state(self.h, _dp(u), None, None))
+
+    def get_up(self) -> np.ndarray:
+        a = self.empty_state()
+        check(self.L.gx_get_up(self.h, _dp(a)))
+        return a
+
+    # -- user_mod plugin surface --
+    def set_gravity_points(self, gm: Sequence[float], pos: Sequence[Sequence[float]]) -> None:
+        gm_a = np.ascontiguousarray(gm, dtype=np.float64)
+        pos_a = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1)
+        check(self.L.gx_set_gravity_points(self.h, len(gm_a), _dp(gm_a), _dp(pos_a)))
+
+    def set_wind_spheres(self, spheres: Sequence[WindSphere]) -> None:
+        arr = (WindSphere * len(spheres))(*spheres)
+        check(self.L.gx_set_wind_spheres(self.h, len(spheres), arr))
+
+    def register_host_bc(self, fn: Optional[Callable[[np.ndarray, int], None]]) -> None:
+        """Slow path mirroring impose_user_bc(u, order): `fn(u, order)` edits u in place."""
+        if fn is None:
+            self._host_bc_ref = None
+            check(self.L.gx_register_host_bc(self.h, _lib.HOST_BC_FN(0), None))
+            return
+        shape = self.shape
+
+        def tramp(ptr, order, _user):
+            n = int(np.prod(shape))
+            arr = np.ctypeslib.as_array(ptr, shape=(n,)).reshape(shape, order="F")
+            fn(arr, int(order))
+
+        self._host_bc_ref = _lib.HOST_BC_FN(tramp)
+        check(self.L.gx_register_host_bc(self.h, self._host_bc_ref, None))
+
+    # -- multi-GPU --
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(_lib.load().gx_comm_unique_id(buf, 128))
+        return buf.raw
+
+    def comm_attach(self, unique_id: bytes, rank: int, nranks: int) -> None:
+        buf = C.create_string_buffer(unique_id, 128)
+        check(self.L.gx_comm_attach(self.h, buf, 128, rank, nranks))
+
+    # -- diagnostics --
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.gx_launch_count(self.h))
+
+    @property
+    def last_elapsed_ms(self) -> float:
+        return float(self.L.gx_last_elapsed_ms(self.h))
+
+    def set_profiling(self, on: bool) -> None:
+        check(self.L.gx_set_profiling(self.h, int(on)))
+
+    def kernel_times(self) -> dict:
+        out = {}
+        for i, name in enumerate(KERNEL_CLASSES):
+            ms = C.c_double(0)
+            n = C.c_int64(0)
+            check(self.L.gx_kernel_time_ms(self.h, i, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
+
+    def interior(self, a: np.ndarray) -> np.ndarray:
+        """Physical cells (1:nx, 1:ny, 1:nz) of a reference-layout array."""
+        return a[..., 2:-2, 2:-2, 2:-2]
+
+
+class Simulation:
+    """The time loop of src/main.f90:94-125 for one block (single GPU) or one rank of many."""
+
+    def __init__(self, block: Block, n_iter_ramp: int = 10):
+        self.b = block
+        self.p = block.p
+        self.n_iter_ramp = n_iter_ramp           # main.f90:97 passes 10
+        self.time = 0.0
+        self.tprint = self.p.dtprint              # init.f90:131
+        self.itprint = 0
+        self.iteration = 1                        # currentIteration, init.f90:125
+        self.on_output: Optional[Callable[["Simulation"], None]] = None
+
+    def initflow(self, u: np.ndarray) -> None:
+        self.b.set_state(u)
+
+    def step(self):
+        dt, dump = self.b.get_timestep(self.iteration, self.n_iter_ramp, self.time, self.tprint)
+        self.b.set_time(self.time)
+        self.b.tstep(dt)
+        self.time += dt
+        if dump:
+            if self.on_output:
+                self.on_output(self)
+            self.tprint += self.p.dtprint
+            self.itprint += 1
+        self.iteration += 1
+        return dt
+
+    def run(self, tmax: Optional[float] = None, max_steps: Optional[int] = None):
+        tmax = self.p.tmax if tmax is None else tmax
+        n = 0
+        while self.time <= tmax and (max_steps is None or n < max_steps):
+            self.step()
+            n += 1
+        return n
+
+
+__all__ = ["Block", "Simulation", "GxError", "WindSphere"]

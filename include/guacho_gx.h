@@ -23,6 +23,12 @@
 
 #include <stdint.h>
 
+#if defined(__GNUC__)
+#define GX_API __attribute__((visibility("default")))
+#else
+#define GX_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -73,37 +79,37 @@ typedef struct gx_solver gx_solver;   /* opaque; one per block (= per GPU / MPI 
 
 /* Replaces the allocation tail of initmain (src/init.f90:144-159): validates the
  * configuration, selects the device and allocates u, up, fluxes and E on it. */
-int gx_create(const gx_config* cfg, gx_solver** out);
+GX_API int gx_create(const gx_config* cfg, gx_solver** out);
 
 /* Frees all device memory (the reference never deallocates; end of main.f90). */
-int gx_destroy(gx_solver* s);
+GX_API int gx_destroy(gx_solver* s);
 
 /* Replaces initflow -> boundaryI -> calcprim at start-up (src/main.f90:73-79):
  * `u` is the caller-owned conserved array in reference layout WITH ghosts.
  * The library uploads it, converts to SoA, and applies boundaryI semantics. */
-int gx_set_state(gx_solver* s, const double* u);
+GX_API int gx_set_state(gx_solver* s, const double* u);
 
 /* Simulation time seen by user boundary functors (globals::time; used by
  * impose_user_bc, EXO/user_mod.f90:131-144). */
-int gx_set_time(gx_solver* s, double time);
+GX_API int gx_set_time(gx_solver* s, double time);
 
 /* Replaces get_timestep (src/hydro_core.f90:623-697): CFL minimum over the
  * block's physical cells (and over all blocks when a communicator is attached),
  * start-up ramp for current_iter <= n_iter, clipping to tprint.  *dump_flag is
  * only ever set to 1 (never cleared), like the reference's intent(out) logical
  * that is assigned only inside the `if`. */
-int gx_get_timestep(gx_solver* s, int32_t current_iter, int32_t n_iter, double current_time,
+GX_API int gx_get_timestep(gx_solver* s, int32_t current_iter, int32_t n_iter, double current_time,
                     double tprint, double* dt, int32_t* dump_flag);
 
 /* Replaces tstep (src/hydro_solver.f90:134-229) for the hydro/MHD part:
  * first-order half step, boundaryII, second-order full step, viscous_copy,
  * boundaryI, primitives.  `dt_cfl` is globals::dt_CFL. */
-int gx_tstep(gx_solver* s, double dt_cfl);
+GX_API int gx_tstep(gx_solver* s, double dt_cfl);
 
 /* Convenience for benchmarking / long runs: n_steps iterations of
  * (get_timestep, tstep, time += dt) entirely driven from the library, as the
  * loop body of src/main.f90:94-125 without output.  In/out: *time, *iter. */
-int gx_run(gx_solver* s, int32_t n_steps, int32_t n_iter_ramp, double* time, int32_t* iter,
+GX_API int gx_run(gx_solver* s, int32_t n_steps, int32_t n_iter_ramp, double* time, int32_t* iter,
            double* last_dt);
 
 /* Implicit "state is on the host" before write_output (src/main.f90:85,112):
@@ -111,10 +117,10 @@ int gx_run(gx_solver* s, int32_t n_steps, int32_t n_iter_ramp, double* time, int
  *   u      : (neq, nx+4, ny+4, nz+4)   conserved, as after boundaryI
  *   primit : (neq, nx+4, ny+4, nz+4)   calcprim(u, primit) over the whole array
  *   temp   : (nx+4, ny+4, nz+4)        Temp from u2prim                         */
-int gx_get_state(gx_solver* s, double* u, double* primit, double* temp);
+GX_API int gx_get_state(gx_solver* s, double* u, double* primit, double* temp);
 
 /* Same for the half-step array `up` (debug/parity aid; globals::up). */
-int gx_get_up(gx_solver* s, double* up);
+GX_API int gx_get_up(gx_solver* s, double* up);
 
 /* ---- user_mod plugin surface (OT/user_mod.f90:43-126, EXO/user_mod.f90) ---- */
 
@@ -122,7 +128,7 @@ int gx_get_up(gx_solver* s, double* up);
  *   s(2:4) -= rho*GM*r_vec/|r|^3,  s(5) -= rho*GM*(v.r_vec)/|r|^3
  * with the reference's cell-centre convention (i - nxtot/2 - 0.5)*dx
  * (EXO/user_mod.f90:158-206).  gm[n], pos[3*n] in code units.  n = 0 disables. */
-int gx_set_gravity_points(gx_solver* s, int32_t n, const double* gm, const double* pos);
+GX_API int gx_set_gravity_points(gx_solver* s, int32_t n, const double* gm, const double* pos);
 
 /* impose_user_bc as a device functor: conserved state re-imposed inside
  * spheres on every boundaryI/boundaryII call (EXO/exoplanet.f90:125-266).
@@ -136,13 +142,13 @@ typedef struct gx_wind_sphere {
   double bdip;                       /* dipole field strength at `radius`        */
   double pas[4];                     /* passive scalars per unit density (npas<=4) */
 } gx_wind_sphere;
-int gx_set_wind_spheres(gx_solver* s, int32_t n, const gx_wind_sphere* sph);
+GX_API int gx_set_wind_spheres(gx_solver* s, int32_t n, const gx_wind_sphere* sph);
 
 /* Slow path for arbitrary user code: host callbacks run on a host copy of the
  * array in reference layout (device -> host -> callback -> device). Excluded
  * from any timed path.  cb(u, order, user) mirrors impose_user_bc(u, order). */
 typedef void (*gx_host_bc_fn)(double* u, int32_t order, void* user);
-int gx_register_host_bc(gx_solver* s, gx_host_bc_fn cb, void* user);
+GX_API int gx_register_host_bc(gx_solver* s, gx_host_bc_fn cb, void* user);
 
 /* ---- multi-GPU: replaces mpi_cart_create / mpi_sendrecv / mpi_allreduce
  * (src/init.f90:103-110, src/boundaries.f90:77-99,292-314,
@@ -151,20 +157,20 @@ int gx_register_host_bc(gx_solver* s, gx_host_bc_fn cb, void* user);
  * r = (cx*nby + cy)*nbz + cz.  The 128-byte id is created on rank 0 and
  * distributed by the host (MPI_Bcast in a Fortran host, torch.distributed in
  * the Python host). */
-int gx_comm_unique_id(void* id_out, int32_t nbytes);
-int gx_comm_attach(gx_solver* s, const void* id, int32_t nbytes, int32_t rank, int32_t nranks);
+GX_API int gx_comm_unique_id(void* id_out, int32_t nbytes);
+GX_API int gx_comm_attach(gx_solver* s, const void* id, int32_t nbytes, int32_t rank, int32_t nranks);
 
 /* ---- diagnostics ---- */
-const char* gx_last_error(void);
+GX_API const char* gx_last_error(void);
 /* number of kernels of this library launched since gx_create (bench evidence) */
-int64_t gx_launch_count(const gx_solver* s);
+GX_API int64_t gx_launch_count(const gx_solver* s);
 /* device time of the last gx_tstep / gx_run in ms, CUDA events on the solver's
  * own stream; per-kernel-class accumulators for the roofline report. */
-double gx_last_elapsed_ms(const gx_solver* s);
-int gx_kernel_time_ms(const gx_solver* s, int32_t which, double* total_ms, int64_t* launches);
-int gx_set_profiling(gx_solver* s, int32_t on);
+GX_API double gx_last_elapsed_ms(const gx_solver* s);
+GX_API int gx_kernel_time_ms(const gx_solver* s, int32_t which, double* total_ms, int64_t* launches);
+GX_API int gx_set_profiling(gx_solver* s, int32_t on);
 /* library build info: "sm_100a fmad=on ..." */
-const char* gx_build_info(void);
+GX_API const char* gx_build_info(void);
 
 #ifdef __cplusplus
 }

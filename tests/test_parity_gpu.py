@@ -1,0 +1,77 @@
+"""GPU parity: CUDA path through the C ABI vs the CPU oracle on the same inputs.
+
+Gate (BASELINE.json north_star / SURVEY §8(c)): per conserved variable
+max|d|/max|ref| <= 1e-12 after one tstep; the strict (-fmad=false) kernels are
+additionally expected to agree to a few ulp.
+"""
+import numpy as np
+import pytest
+
+from guacho_b200.config import (Params, ot_shipped, SOLVER_HLL, SOLVER_HLLC, SOLVER_HLLE, SOLVER_HLLD,
+                                ALL_LIMITERS, LIMITER_MINMOD, BC_OUTFLOW, BC_CLOSED, BC_PERIODIC)
+from tests.oracle_lib import U, UP, PRIMIT
+from tests.util import global_ic, oracle_from_ic, rel_err_per_var, interior
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def run_pair(p: Params, problem="ot", nsteps=1, **ickw):
+    from guacho_b200.solver import Block
+    g = global_ic(p, problem, **ickw)
+    o = oracle_from_ic(p.replace(MPI_NBX=1, MPI_NBY=1, MPI_NBZ=1), g)
+    with Block(p.replace(MPI_NBX=1, MPI_NBY=1, MPI_NBZ=1)) as b:
+        b.set_state(g)
+        t, it = 0.0, 1
+        for _ in range(nsteps):
+            dt_o, _ = o.get_timestep(it, 10, t, 1e300)
+            dt_g, _ = b.get_timestep(it, 10, t, 1e300)
+            assert abs(dt_g - dt_o) <= 1e-13 * abs(dt_o), (dt_g, dt_o)
+            assert o.tstep(dt_o) == 0
+            b.set_time(t)
+            b.tstep(dt_o)
+            t += dt_o
+            it += 1
+        ug, wg = b.get_state(u=True, primit=True)
+    uo = o.get_block(0, U)
+    wo = o.get_block(0, PRIMIT)
+    return interior(ug), interior(uo), interior(wg), interior(wo)
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_ot_shipped_grid_one_step(strict):
+    p = ot_shipped(nxtot=128, nytot=128, nztot=2, zmax=2.0 / 128, MPI_NBX=1, strict_fp=strict)
+    ug, uo, wg, wo = run_pair(p)
+    err = rel_err_per_var(ug, uo)
+    assert err.max() <= (1e-15 if strict else TOL), err
+    assert rel_err_per_var(wg, wo).max() <= TOL
+
+
+@pytest.mark.parametrize("solver,mhd,cd", [(SOLVER_HLLD, True, True), (SOLVER_HLLD, True, False), (SOLVER_HLLE, True, True),
+                                            (SOLVER_HLL, False, False), (SOLVER_HLLC, False, False)])
+def test_solvers_random_field_3d(solver, mhd, cd):
+    p = Params(nxtot=32, nytot=24, nztot=20, zmax=1.0, mhd=mhd, riemann_solver=solver, enable_flux_cd=cd, strict_fp=True)
+    ug, uo, wg, wo = run_pair(p, "random", nsteps=3)
+    err = rel_err_per_var(ug, uo)
+    assert err.max() <= TOL, err
+
+
+@pytest.mark.parametrize("lim", ALL_LIMITERS)
+def test_limiters(lim):
+    p = Params(nxtot=24, nytot=20, nztot=16, zmax=1.0, slope_limiter=lim, strict_fp=True)
+    ug, uo, _, _ = run_pair(p, "random", nsteps=2)
+    assert rel_err_per_var(ug, uo).max() <= TOL
+
+
+@pytest.mark.parametrize("bc", [BC_OUTFLOW, BC_CLOSED])
+def test_physical_boundaries(bc):
+    p = Params(nxtot=24, nytot=20, nztot=16, zmax=1.0, bc_left=bc, bc_right=bc, bc_bottom=bc, bc_top=bc, bc_out=bc, bc_in=bc, strict_fp=True)
+    ug, uo, _, _ = run_pair(p, "blast", nsteps=3, r0=0.3)
+    assert rel_err_per_var(ug, uo).max() <= TOL
+
+
+def test_eight_wave_and_viscosity_and_passives():
+    p = Params(nxtot=24, nytot=20, nztot=16, zmax=1.0, enable_flux_cd=False, eight_wave=True, eta=0.01, npas=2, strict_fp=True)
+    ug, uo, _, _ = run_pair(p, "random", nsteps=3)
+    assert rel_err_per_var(ug, uo).max() <= TOL
