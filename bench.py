@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py — Guacho hydro/MHD time-step throughput on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric (BASELINE.json): MHD zone-updates/s (HLLD + flux-CD, FP64); one zone-update = one
+full tstep (both stages, boundaries, CFL) of one physical cell.  Workload at N=1:
+BASELINE.json configs[1], the 3-D Orszag-Tang vortex on 256^3 (OT initial conditions
+extruded along z, periodic, minmod, cfl 0.2), synthetic data generated on the host.
+N>1: weak scaling, the same 256^3 block per GPU, z-slab decomposition, NCCL halo exchange.
+
+One JSON line on stdout (rank 0).  `value` = device-resident throughput (CUDA events on
+the solver's stream, max over ranks); `e2e` = the same metric through the C ABI with HOST
+buffers: every step uploads u (pinned host, reference layout), runs get_timestep + tstep
+and downloads u again, all inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from guacho_b200.config import Params, ot_3d  # noqa: E402
+from guacho_b200 import problems  # noqa: E402
+
+METRIC = "MHD zone-updates/s (HLLD + flux-CD, FP64)"
+UNIT = "zone-updates/s"
+BYTES_PER_ZONE = 320.0      # algorithmic: 5*neq doubles, neq = 8
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload(n_per_gpu: int, world: int) -> Params:
+    # weak scaling: the same n^3 block per GPU, stacked along z
+    return ot_3d(n_per_gpu, nztot=n_per_gpu * world, zmax=1.0 * world)
+
+
+def cpu_reference(p_block: Params, steps: int, warmup: int, threads: int):
+    """The reference's CPU path (C++ restatement, oracle/, -O3 -ffp-contract=off) on a bounded
+    sample of the workload: a z-slab of the same initial conditions (OT is z-invariant, so the
+    per-zone work is identical), one block per thread like the reference's MPI ranks."""
+    from tests.oracle_lib import Oracle
+    nzs = 16
+    p = p_block.replace(nztot=nzs, zmax=p_block.zmax * nzs / p_block.nztot, MPI_NBX=threads, MPI_NBY=1, MPI_NBZ=1)
+    o = Oracle(p, fast=True, threads=threads)
+    g = problems.orszag_tang(p.replace(MPI_NBX=1), (0, 0, 0))
+    o.scatter_u(g)
+    o.start()
+    o.iter = 11                                   # past the 10-step CFL ramp (hydro_core.f90:677-682)
+    o.run_timed(max(1, warmup))
+    sec = o.run_timed(steps)
+    zones = p.nxtot * p.nytot * p.nztot
+    sample = f"{p.nxtot}x{p.nytot}x{nzs} slab of the same OT field, {threads} blocks x 1 thread (x-split like the reference's MPI), {steps} steps after {max(1, warmup)} warm-up"
+    return zones * steps / sec, sec / steps * 1e3, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    p = workload(args.n, 1)
+    steps = max(1, min(args.steps, 3))
+    v, ms, sample = cpu_reference(p, steps, min(args.warmup, 1), threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"3-D Orszag-Tang {args.n}^3 HLLD+flux-CD minmod periodic (CPU: bounded slab sample)", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is Fortran+MPI and cannot be built in this image (no Fortran compiler/MPI); this is the line-faithful C++ restatement in oracle/",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=256, help="cells per side of the per-GPU block")
+    ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strict", action="store_true", help="use the -fmad=false bit-comparison kernels")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from guacho_b200.distributed import init_process_group, make_rank_block
+    from guacho_b200.decomp import coords_of, halo_bytes_per_step
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the step has no CPU fallback (use --impl reference for the CPU path)")
+    args.warmup = max(args.warmup, 3)
+    rank, local_rank, world = init_process_group()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+
+    p = workload(args.n, world).replace(strict_fp=args.strict)
+    nb = (1, 1, world)
+    blk = make_rank_block(p, rank, world, local_rank, nb=nb)
+    pb = blk.p
+    coords = coords_of(rank, nb)
+    u0 = problems.orszag_tang(pb, coords)
+    zones_rank = pb.nx * pb.ny * pb.nz
+    zones_total = zones_rank * world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident throughput ----------------
+    blk.set_state(u0)
+    tsim, it = 0.0, 1
+    tsim, it, _ = blk.run(args.warmup, tsim, it)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = blk.launch_count
+    tsim, it, last_dt = blk.run(args.steps, tsim, it)
+    ms = blk.last_elapsed_ms
+    l1 = blk.launch_count
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms)
+    value = zones_total * args.steps / (ms * 1e-3)
+
+    # per-kernel-class device times (separate pass, CUDA events around each launch on the solver's stream)
+    blk.set_profiling(True)
+    tsim, it, _ = blk.run(min(args.steps, 5), tsim, it)
+    ktimes = blk.kernel_times()
+    nprof = min(args.steps, 5)
+    blk.set_profiling(False)
+
+    # ---------------- end to end through the C ABI with host buffers ----------------
+    e2e_steps = args.e2e_steps if args.e2e_steps is not None else max(3, min(args.steps, 10))
+    pinned = torch.empty(int(np.prod(pb.block_shape())), dtype=torch.float64, pin_memory=True)
+    uh = pinned.numpy().reshape(pb.block_shape(), order="F")
+    uh[...] = blk.get_state()
+    t_e, it_e = tsim, it
+    for _ in range(2 if e2e_steps > 0 else 0):   # warm-up
+        blk.set_state(uh); dt, _d = blk.get_timestep(it_e, 10, t_e, 1e300); blk.tstep(dt); blk.get_state_into(uh); t_e += dt; it_e += 1
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        blk.set_state(uh)                                   # H2D: u in reference layout (with ghosts)
+        dt, _d = blk.get_timestep(it_e, 10, t_e, 1e300)     # D2H: CFL dt
+        blk.tstep(dt)
+        blk.get_state_into(uh)                              # D2H: updated u
+        t_e += dt; it_e += 1
+    torch.cuda.synchronize()
+    e2e_sec = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = zones_total * e2e_steps / e2e_sec if e2e_steps > 0 else None
+    state_bytes = int(uh.nbytes)
+    finite = bool(np.isfinite(uh).all())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak_gbs, peak_src = measured_peaks()
+    step_ms = ms / args.steps
+    achieved_gbs = BYTES_PER_ZONE * zones_rank / (step_ms * 1e-3) / 1e9
+    flux_ms, flux_n = ktimes["flux"]
+    tot_prof = sum(v[0] for v in ktimes.values())
+    roofline = {
+        "bound": "hbm", "achieved": achieved_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": achieved_gbs / peak_gbs, "traffic": None,
+        "peak_source": peak_src,
+        "definition": "320 B algorithmic per zone-update x zones per GPU / whole-step device time (all kernels of one tstep)",
+        "kernel_share": {k: (v[0] / tot_prof if tot_prof > 0 else None) for k, v in ktimes.items()},
+        "kernel_ms_per_step": {k: v[0] / nprof for k, v in ktimes.items()},
+        "dominant_kernel": "flux sweeps (k_flux<HLLD,minmod>)", "dominant_avg_launch_ms": (flux_ms / flux_n if flux_n else None),
+    }
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, _ms, sample = cpu_reference(workload(args.n, 1), 2, 1, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"3-D Orszag-Tang {args.n}^3 per GPU (BASELINE configs[1]), HLLD + flux-CD, minmod, periodic, cfl 0.2",
+                   "grid_total": [pb.nxtot, pb.nytot, pb.nztot], "blocks": list(nb), "neq": pb.neq,
+                   "kernels": "strict (-fmad=false)" if args.strict else "fast (-fmad=true)",
+                   "l2": "working set (u,up,W,F,E > 3 GB per GPU) exceeds the 126 MB L2; no flush needed",
+                   "halo_bytes_per_step_per_gpu": halo_bytes_per_step(pb)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes + 16,
+                "steps": e2e_steps, "ms_per_step": (e2e_sec / e2e_steps * 1e3 if e2e_steps > 0 else None),
+                "path": "gx_set_state(host u) -> gx_get_timestep -> gx_tstep -> gx_get_state(host u) through libguacho_gx.so"},
+        "gpu_launches": int(l1 - l0),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "finite": finite, "last_dt": last_dt,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -39,10 +39,14 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in _sources())
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build_library(force: bool = False, verbose: bool = False, extra=(), out: str = LIB) -> str:
+    """`extra`/`out` build tuning variants (e.g. -DGX_FLUX_MINBLOCKS=6) next to the default library."""
+    global BUILD
+    if out == LIB and not force and not needs_build():
         return LIB
     nvcc = _nvcc()
+    if out != LIB:
+        BUILD = os.path.join(HERE, "csrc", "build_" + os.path.basename(out).replace(".so", ""))
     os.makedirs(BUILD, exist_ok=True)
     jobs = [
         ("gx_kernels_strict.o", "gx_kernels.cu", ["-fmad=false", "-DGX_FLAVOUR_STRICT"]),
@@ -50,19 +54,21 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         ("gx_api.o", "gx_api.cu", ["-fmad=false"]),
     ]
     procs = []
-    for obj, src, extra in jobs:
-        cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", os.path.join(BUILD, obj)]
+    for obj, src, flags in jobs:
+        cmd = [nvcc] + ARCH + COMMON + flags + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", os.path.join(BUILD, obj)]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if verbose or p.returncode:
-            sys.stderr.write(out)
+            sys.stderr.write(log)
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + [os.path.join(BUILD, j[0]) for j in jobs] + ["-ldl"]
+    cmd = [nvcc] + ARCH + ["-shared", "-o", out] + [os.path.join(BUILD, j[0]) for j in jobs] + ["-ldl"]
     subprocess.check_call(cmd)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, extra=defs, out=(os.path.abspath(outs[0]) if outs else LIB)))

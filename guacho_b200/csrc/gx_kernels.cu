@@ -85,8 +85,11 @@ template <int D> __device__ __forceinline__ constexpr int comp(int c) {
 
 // One thread = one interface (upper face of cell i,j,k in direction D).
 // Faces the update never reads are skipped.
+#ifndef GX_FLUX_MINBLOCKS
+#define GX_FLUX_MINBLOCKS 4
+#endif
 template <int SOLVER, int LIM, int ORDER, int D>
-__global__ void __launch_bounds__(128) k_flux(const StepArgs A, const double* __restrict__ W, double* __restrict__ F, int* errflag) {
+__global__ void __launch_bounds__(128, GX_FLUX_MINBLOCKS) k_flux(const StepArgs A, const double* __restrict__ W, double* __restrict__ F, int* errflag) {
   constexpr bool MHD = (SOLVER == GX_SOLVER_HLLE || SOLVER == GX_SOLVER_HLLD);
   constexpr int NQ = MHD ? 8 : 5;
   const Grid& g = A.g;

@@ -22,15 +22,73 @@ struct Phys {            // the scalar `parameter`s the cell routines read
 
 __device__ __forceinline__ double sign1(double x) { return copysign(1.0, x); }   // Fortran sign(1.,x)
 
+// ---- division / square root policy ----
+// strict build (GX_FLAVOUR_STRICT, -fmad=false): IEEE a/b and sqrt, one per occurrence in the
+// reference expression, so results are bit-comparable with the reference arithmetic.
+// fast build: divisions by the same denominator share ONE reciprocal (MUFU.RCP64H seed + a
+// third-order Newton step, ~1 ulp) and square roots come from MUFU.RSQ64H + two coupled
+// Newton steps that also yield 1/sqrt.  FP64 division is ~12 FP64-pipe instructions on
+// sm_100a and HLLD has 25 of them per interface, so this removes most of the FP64 work.
+#if defined(GX_FLAVOUR_FAST)
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));      // rel. error <= 2^-23
+  double e = fma(-x, r, 1.0);
+  double t = fma(e, e, e);                                    // e + e^2
+  return fma(r, t, r);                                        // error ~ e^3 = 2^-69
+}
+// s = sqrt(x), rs = 1/sqrt(x) for x > 0 (x == 0 -> s = 0, rs = inf-like large is never used)
+__device__ __forceinline__ void fast_sqrt_rsqrt(double x, double& s, double& rs) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));    // rel. error <= 2^-22
+  double g = x * y, h = 0.5 * y;
+  double r = fma(-h, g, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-h, g, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  s = (x > 0.0) ? g : ((x == 0.0) ? 0.0 : g);
+  rs = h + h;
+}
+__device__ __forceinline__ double gx_sqrt(double x) { double s, rs; fast_sqrt_rsqrt(x, s, rs); return s; }
+// discriminant of the fast-speed formula: >= 0 analytically, may round to -eps with re-associated arithmetic
+__device__ __forceinline__ double gx_sqrt_disc(double x) { return gx_sqrt(fmax(x, 0.0)); }
+struct Den {                      // a denominator used one or more times
+  double inv;
+  __device__ __forceinline__ explicit Den(double b) : inv(fast_rcp(b)) {}
+  __device__ __forceinline__ double div(double a) const { return a * inv; }
+};
+struct SqrtDen {                  // sqrt(x) that is also used as a denominator
+  double s, rs;
+  __device__ __forceinline__ explicit SqrtDen(double x) { fast_sqrt_rsqrt(x, s, rs); }
+  __device__ __forceinline__ double div(double a) const { return a * rs; }
+};
+__device__ __forceinline__ double sqrt_prod(const SqrtDen& a, const SqrtDen& b, double) { return a.s * b.s; }
+#else
+__device__ __forceinline__ double gx_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ double gx_sqrt_disc(double x) { return sqrt(x); }
+struct Den {
+  double b;
+  __device__ __forceinline__ explicit Den(double b_) : b(b_) {}
+  __device__ __forceinline__ double div(double a) const { return a / b; }
+};
+struct SqrtDen {
+  double s;
+  __device__ __forceinline__ explicit SqrtDen(double x) : s(sqrt(x)) {}
+  __device__ __forceinline__ double div(double a) const { return a / s; }
+};
+__device__ __forceinline__ double sqrt_prod(const SqrtDen&, const SqrtDen&, double xy) { return sqrt(xy); }
+#endif
+
 // ---- u2prim: src/hydro_core.f90:46-129 (dynamic variables only; passives are copies) ----
 // `pas0` is the first passive (needed by EOS_H_RATE only).
 template <bool MHD>
 __device__ __forceinline__ void u2prim(const Phys& P, const double (&u)[8], double (&w)[8], double pas0, double& T) {
   double r = fmax(u[0], 1e-15);
   w[0] = r;
-  w[1] = u[1] / r;
-  w[2] = u[2] / r;
-  w[3] = u[3] / r;
+  const Den dr(r);
+  w[1] = dr.div(u[1]);
+  w[2] = dr.div(u[2]);
+  w[3] = dr.div(u[3]);
   double ek = 0.5 * r * (w[1] * w[1] + w[2] * w[2] + w[3] * w[3]);
   double p;
   if (MHD) p = (u[4] - ek - 0.5 * (u[5] * u[5] + u[6] * u[6] + u[7] * u[7])) / P.cv;
@@ -53,12 +111,13 @@ __device__ __forceinline__ void u2prim(const Phys& P, const double (&u)[8], doub
 }
 
 // ---- wave speeds: src/hydro_core.f90:544-604 ----
-__device__ __forceinline__ double csound(const Phys& P, double p, double d) { return sqrt(P.gamma * p / d); }
+__device__ __forceinline__ double csound(const Phys& P, double p, double d) { return gx_sqrt(Den(d).div(P.gamma * p)); }
 
 __device__ __forceinline__ double cfastX(const Phys& P, const double (&w)[8]) {
   double b2 = w[5] * w[5] + w[6] * w[6] + w[7] * w[7];
-  double cs2va2 = (P.gamma * w[4] + b2) / w[0];
-  return sqrt(0.5 * (cs2va2 + sqrt(cs2va2 * cs2va2 - 4. * P.gamma * w[4] * (w[5] * w[5]) / w[0] / w[0])));
+  const Den rho(w[0]);
+  double cs2va2 = rho.div(P.gamma * w[4] + b2);
+  return gx_sqrt(0.5 * (cs2va2 + gx_sqrt_disc(cs2va2 * cs2va2 - rho.div(rho.div(4. * P.gamma * w[4] * (w[5] * w[5]))))));
 }
 
 // CFL form (src/hydro_core.f90:568-581): fast speed along each axis
@@ -67,9 +126,10 @@ __device__ __forceinline__ void cfast3(const Phys& P, double p, double d, double
   double b2 = bx * bx + by * by + bz * bz;
   double gpb = P.gamma * p + b2;
   double gp4 = 4. * P.gamma * p;
-  cx = sqrt(0.5 * (gpb + sqrt(gpb * gpb - gp4 * bx * bx)) / d);
-  cy = sqrt(0.5 * (gpb + sqrt(gpb * gpb - gp4 * by * by)) / d);
-  cz = sqrt(0.5 * (gpb + sqrt(gpb * gpb - gp4 * bz * bz)) / d);
+  const Den dd(d);
+  cx = gx_sqrt(dd.div(0.5 * (gpb + gx_sqrt_disc(gpb * gpb - gp4 * bx * bx))));
+  cy = gx_sqrt(dd.div(0.5 * (gpb + gx_sqrt_disc(gpb * gpb - gp4 * by * by))));
+  cz = gx_sqrt(dd.div(0.5 * (gpb + gx_sqrt_disc(gpb * gpb - gp4 * bz * bz))));
 }
 
 // ---- prim2f / prim2u: src/hydro_core.f90:331-476 (non-split branches) ----
@@ -197,8 +257,9 @@ __device__ __forceinline__ int riemann_hll(const Phys& P, const double (&wl)[8],
   prim2f<MHD>(P, wl, fL); prim2f<MHD>(P, wr, fR);
   prim2u<MHD>(P, wl, uL); prim2u<MHD>(P, wr, uR);
   const int n = MHD ? 8 : 5;
+  const Den ds(sr - sl);
 #pragma unroll
-  for (int q = 0; q < n; ++q) ff[q] = (sr * fL[q] - sl * fR[q] + sl * sr * (uR[q] - uL[q])) / (sr - sl);
+  for (int q = 0; q < n; ++q) ff[q] = ds.div(sr * fL[q] - sl * fR[q] + sl * sr * (uR[q] - uL[q]));
   I.mode = PAS_HLL;
   return 0;
 }
@@ -260,11 +321,12 @@ __device__ __forceinline__ Star hlld_star(const double (&q)[8], double bx, doubl
   if (den == 0) {                      // hlld.f90:119-126 degenerate guard
     s.v = q[2]; s.w = q[3]; s.by = 0.; s.bz = 0.;
   } else {
-    s.v = q[2] - bx * q[6] * sMmu / den;
-    s.w = q[3] - bx * q[7] * sMmu / den;
+    const Den dn(den);
+    s.v = q[2] - dn.div(bx * q[6] * sMmu);
+    s.w = q[3] - dn.div(bx * q[7] * sMmu);
     double num = q[0] * (smu * smu) - bx * bx;
-    s.by = q[6] * num / den;
-    s.bz = q[7] * num / den;
+    s.by = dn.div(q[6] * num);
+    s.bz = dn.div(q[7] * num);
   }
   return s;
 }
@@ -290,16 +352,18 @@ __device__ __forceinline__ int riemann_hlld(const Phys& P, const double (&wl)[8]
   double srmur = sr - wr[1];
   double rholul = wl[0] * wl[1];
   double rhorur = wr[0] * wr[1];
-  double den = srmur * wr[0] - slmul * wl[0];
-  double sM = (srmur * rhorur - slmul * rholul - pTR + pTL) / den;
+  const Den den(srmur * wr[0] - slmul * wl[0]);
+  double sM = den.div(srmur * rhorur - slmul * rholul - pTR + pTL);
   double srmsM = sr - sM;
   double slmsM = sl - sM;
-  double rhostl = wl[0] * slmul / slmsM;
-  double rhostr = wr[0] * srmur / srmsM;
-  double sql = sqrt(rhostl), sqr = sqrt(rhostr);
-  double sstl = sM - fabs(bx) / sql;
-  double sstr = sM + fabs(bx) / sqr;
-  double pst = (srmur * wr[0] * pTL - slmul * wl[0] * pTR + wl[0] * wr[0] * srmur * slmul * (wr[1] - wl[1])) / den;
+  const Den dslm(slmsM), dsrm(srmsM);
+  double rhostl = dslm.div(wl[0] * slmul);
+  double rhostr = dsrm.div(wr[0] * srmur);
+  const SqrtDen SQL(rhostl), SQR(rhostr);
+  const double sql = SQL.s, sqr = SQR.s;
+  double sstl = sM - SQL.div(fabs(bx));
+  double sstr = sM + SQR.div(fabs(bx));
+  double pst = den.div(srmur * wr[0] * pTL - slmul * wl[0] * pTR + wl[0] * wr[0] * srmur * slmul * (wr[1] - wl[1]));
 
   // Which side supplies the outer state: L for UL*, UL**; R for UR*, UR**.
   // Region order as in the reference: sstl>=0, sstr<=0, sM>=0, sM<=0.
@@ -314,12 +378,12 @@ __device__ __forceinline__ int riemann_hlld(const Phys& P, const double (&wl)[8]
 
   double vs, ws, bys, bzs, vdb_ss = 0.;     // state used in the flux (star or double-star)
   if (dstar) {
-    double dd = sql + sqr;
-    double sq2 = sqrt(rhostl * rhostr);
-    vs = (sql * SL.v + sqr * SR.v + (SR.by - SL.by) * signBx) / dd;
-    ws = (sql * SL.w + sqr * SR.w + (SR.bz - SL.bz) * signBx) / dd;
-    bys = (sql * SR.by + sqr * SL.by + sq2 * (SR.v - SL.v) * signBx) / dd;
-    bzs = (sql * SR.bz + sqr * SL.bz + sq2 * (SR.w - SL.w) * signBx) / dd;
+    const Den dd(sql + sqr);
+    double sq2 = sqrt_prod(SQL, SQR, rhostl * rhostr);
+    vs = dd.div(sql * SL.v + sqr * SR.v + (SR.by - SL.by) * signBx);
+    ws = dd.div(sql * SL.w + sqr * SR.w + (SR.bz - SL.bz) * signBx);
+    bys = dd.div(sql * SR.by + sqr * SL.by + sq2 * (SR.v - SL.v) * signBx);
+    bzs = dd.div(sql * SR.bz + sqr * SL.bz + sq2 * (SR.w - SL.w) * signBx);
     vdb_ss = sM * bx + vs * bys + ws * bzs;
   }
 
@@ -328,7 +392,7 @@ __device__ __forceinline__ int riemann_hlld(const Phys& P, const double (&wl)[8]
     double el = hlld_energy(P, wl, bx);
     double vdotb = wl[1] * bx + wl[2] * wl[6] + wl[3] * wl[7];
     double vsdotbs = sM * bx + SL.v * SL.by + SL.w * SL.bz;
-    double estl = (slmul * el - pTL * wl[1] + pst * sM + bx * (vdotb - vsdotbs)) / slmsM;
+    double estl = dslm.div(slmul * el - pTL * wl[1] + pst * sM + bx * (vdotb - vsdotbs));
     rhost = rhostl;
     if (dstar) { es = estl - sql * (vsdotbs - vdb_ss) * signBx; }
     else { es = estl; vs = SL.v; ws = SL.w; bys = SL.by; bzs = SL.bz; vdb_ss = vsdotbs; }
@@ -337,7 +401,7 @@ __device__ __forceinline__ int riemann_hlld(const Phys& P, const double (&wl)[8]
     double er = hlld_energy(P, wr, bx);
     double vdotb = wr[1] * bx + wr[2] * wr[6] + wr[3] * wr[7];
     double vsdotbs = sM * bx + SR.v * SR.by + SR.w * SR.bz;
-    double estr = (srmur * er - pTR * wr[1] + pst * sM + bx * (vdotb - vsdotbs)) / srmsM;
+    double estr = dsrm.div(srmur * er - pTR * wr[1] + pst * sM + bx * (vdotb - vsdotbs));
     rhost = rhostr;
     if (dstar) { es = estr + sqr * (vsdotbs - vdb_ss) * signBx; }
     else { es = estr; vs = SR.v; ws = SR.w; bys = SR.by; bzs = SR.bz; vdb_ss = vsdotbs; }

@@ -12,7 +12,7 @@ import os
 from .config import GxConfig
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libguacho_gx.so")
+LIB_PATH = os.environ.get("GUACHO_GX_LIB") or os.path.join(HERE, "libguacho_gx.so")   # override: tuning variants only
 
 GX_OK = 0
 ERRORS = {-1: "GX_EINVAL", -2: "GX_ENODEVICE", -3: "GX_ECUDA", -4: "GX_ENOMEM",
