@@ -53,16 +53,29 @@ def build_library(force: bool = False, verbose: bool = False, extra=(), out: str
         ("gx_kernels_fast.o", "gx_kernels.cu", ["-fmad=true", "-DGX_FLAVOUR_FAST"]),
         ("gx_api.o", "gx_api.cu", ["-fmad=false"]),
     ]
-    procs = []
-    for obj, src, flags in jobs:
-        cmd = [nvcc] + ARCH + COMMON + flags + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", os.path.join(BUILD, obj)]
-        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for cmd, p in procs:
+    # fused stage kernels: one translation unit per (flavour, Riemann solver); HLLD first (largest)
+    for solver in (4, 3, 2, 1):
+        jobs.append((f"gx_stage_fast_{solver}.o", "gx_stage.cu", ["-fmad=true", "-DGX_FLAVOUR_FAST", f"-DGX_STAGE_SOLVER={solver}"]))
+        jobs.append((f"gx_stage_strict_{solver}.o", "gx_stage.cu", ["-fmad=false", "-DGX_FLAVOUR_STRICT", f"-DGX_STAGE_SOLVER={solver}"]))
+    if os.environ.get("GX_DEV_MINMOD_ONLY"):
+        extra = list(extra) + ["-DGX_DEV_MINMOD_ONLY"]
+    cmds = [[nvcc] + ARCH + COMMON + flags + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", os.path.join(BUILD, obj)]
+            for obj, src, flags in jobs]
+    njobs = max(1, min(len(cmds), os.cpu_count() or 4))
+    running, failed = [], None
+    pending = list(cmds)
+    while pending or running:
+        while pending and len(running) < njobs:
+            cmd = pending.pop(0)
+            running.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        cmd, p = running.pop(0)
         log, _ = p.communicate()
         if verbose or p.returncode:
             sys.stderr.write(log)
-        if p.returncode:
-            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+        if p.returncode and failed is None:
+            failed = cmd
+    if failed:
+        raise RuntimeError("nvcc failed: " + " ".join(failed))
     cmd = [nvcc] + ARCH + ["-shared", "-o", out] + [os.path.join(BUILD, j[0]) for j in jobs] + ["-ldl"]
     subprocess.check_call(cmd)
     return out

@@ -6,6 +6,7 @@
 #include <nccl.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -73,6 +74,8 @@ struct gx_solver {
   struct DevScalars { unsigned long long dtmin_bits; int err; int pad; }* dscal = nullptr;   // device
   DevScalars* hscal = nullptr;                                // pinned host mirror
   bool have_state = false;
+  bool fused = false;      // fused stage kernels (gx_stage.cu); otherwise the pass-per-routine kernels
+  int kz = 16;             // planes one CTA of the fused stage kernel marches through
   double time = 0.0;
   // block topology (mpi_cart_shift results; -1 = MPI_PROC_NULL)
   int nb[3] = {1, 1, 1}, co[3] = {0, 0, 0};
@@ -417,10 +420,16 @@ int gx_create(const gx_config* c, gx_solver** out) {
 #define ALLOC(p, n) do { cudaError_t e_ = cudaMalloc((void**)&(p), (n)); if (e_ != cudaSuccess) { std::string m = cudaGetErrorString(e_); gx_destroy(s); return fail(GX_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", (size_t)(n), m.c_str()); } cudaMemsetAsync((p), 0, (n), 0); } while (0)
   cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   const size_t var_bytes = (size_t)g.vs * sizeof(double);
+  // fused stage kernels cover the dynamic variables; passives, the 8-wave / user sources and
+  // eta != 0 (viscous_copy needs up's stale half-step ghosts) take the pass-per-routine kernels
+  s->fused = c->npas == 0 && !c->eight_wave && !c->user_source_terms && c->eta == 0.0 && !getenv("GX_NO_FUSED");
+  if (const char* e = getenv("GX_KZ")) s->kz = std::max(1, atoi(e));
   ALLOC(s->U, var_bytes * g.neq);
   ALLOC(s->UP, var_bytes * g.neq);
-  ALLOC(s->W, var_bytes * g.neq);
-  ALLOC(s->F, var_bytes * g.neq * 3);
+  if (!s->fused) {                                   // primitives and face fluxes only exist in HBM on the unfused path
+    ALLOC(s->W, var_bytes * g.neq);
+    ALLOC(s->F, var_bytes * g.neq * 3);
+  }
   if (c->enable_flux_cd) ALLOC(s->E, var_bytes * 3);
   ALLOC(s->dscal, sizeof(gx_solver::DevScalars));
   cudaMallocHost((void**)&s->hscal, sizeof(gx_solver::DevScalars));
@@ -465,10 +474,22 @@ int gx_destroy(gx_solver* s) {
   return GX_OK;
 }
 
-static int reset_scalars(gx_solver* s) {
-  gx_solver::DevScalars init; init.dtmin_bits = 0x7FF0000000000000ull; init.err = 0; init.pad = 0;   // +inf
+static int reset_scalars(gx_solver* s) {          // CFL minimum := +inf, solver error flag := 0 (new state)
+  gx_solver::DevScalars init; init.dtmin_bits = 0x7FF0000000000000ull; init.err = 0; init.pad = 0;
   *s->hscal = init;
   CUDA_TRY(cudaMemcpyAsync(s->dscal, s->hscal, sizeof init, cudaMemcpyHostToDevice, s->stream));
+  return GX_OK;
+}
+static int reset_dtmin(gx_solver* s) {            // CFL minimum := +inf; the error flag stays sticky
+  CUDA_TRY(cudaMemsetAsync(&s->dscal->dtmin_bits, 0x7f, sizeof(unsigned long long), s->stream));   // 0x7f7f.. ~ 1.4e306
+  return GX_OK;
+}
+static int ensure_array(gx_solver* s, double** p, size_t nvar) {
+  if (*p) return GX_OK;
+  const size_t bytes = (size_t)s->A.g.vs * sizeof(double) * nvar;
+  cudaError_t e = cudaMalloc((void**)p, bytes);
+  if (e != cudaSuccess) return fail(GX_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+  CUDA_TRY(cudaMemsetAsync(*p, 0, bytes, s->stream));
   return GX_OK;
 }
 
@@ -476,7 +497,7 @@ static int reset_scalars(gx_solver* s) {
 static int finish_u(gx_solver* s) {
   int rc = apply_boundaries(s, s->U, s->A.g.neq, 1, 0); if (rc) return rc;
   rc = apply_user_bc(s, s->U, 1); if (rc) return rc;
-  rc = reset_scalars(s); if (rc) return rc;
+  rc = reset_dtmin(s); if (rc) return rc;
   { LaunchScope ls(s, gx::KC_PRIM); s->K->calcprim(s->A, s->U, s->W, nullptr, &s->dscal->dtmin_bits, 1, s->stream); }
   CUDA_TRY(cudaGetLastError());
   return GX_OK;
@@ -486,6 +507,7 @@ int gx_set_state(gx_solver* s, const double* u) {
   if (!s || !u) return fail(GX_EINVAL, "null argument");
   cudaSetDevice(s->device);
   int rc = upload_aos(s, u, s->U, s->A.g.neq); if (rc) return rc;
+  rc = reset_scalars(s); if (rc) return rc;
   rc = finish_u(s); if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   collect_timed(s);
@@ -516,7 +538,40 @@ int gx_get_timestep(gx_solver* s, int32_t current_iter, int32_t n_iter, double c
   return GX_OK;
 }
 
+// tstep with the fused stage kernels: per stage one k_stage launch (prim + 3 sweeps + E + update)
+// and, with flux-CD, the E ghost layer + k_bupdate.  Same sequence as hydro_solver.f90:134-229.
+static int tstep_enqueue_fused(gx_solver* s, double dt_cfl) {
+  const gx::KernelTable* K = s->K;
+  const StepArgs& A = s->A;
+  const int neq = A.g.neq;
+  const double dtm = dt_cfl / 2.;
+  const bool cfl_in_step = !s->cfg.bc_user;          // a user BC may overwrite physical cells after the update
+  int rc;
+  { LaunchScope ls(s, gx::KC_STAGE1); rc = K->stage(A, 1, dtm, s->U, s->U, s->UP, s->E, s->kz, nullptr, 0, &s->dscal->err, s->stream); } if (rc) return fail(rc, "stage-1 launch");
+  if (A.flux_cd) {
+    rc = apply_boundaries(s, s->E, 3, 1, 1); if (rc) return rc;
+    { LaunchScope ls(s, gx::KC_BUPDATE); K->bupdate(A, dtm, s->U, s->E, s->UP, nullptr, 0, s->stream); }
+  }
+  rc = apply_boundaries(s, s->UP, neq, 2, 0); if (rc) return rc;          // boundaryII :169
+  rc = apply_user_bc(s, s->UP, 2); if (rc) return rc;
+  rc = reset_dtmin(s); if (rc) return rc;
+  { LaunchScope ls(s, gx::KC_STAGE2); rc = K->stage(A, 2, dt_cfl, s->UP, s->U, s->U, s->E, s->kz, &s->dscal->dtmin_bits, cfl_in_step && !A.flux_cd, &s->dscal->err, s->stream); } if (rc) return fail(rc, "stage-2 launch");
+  if (A.flux_cd) {
+    rc = apply_boundaries(s, s->E, 3, 1, 1); if (rc) return rc;
+    { LaunchScope ls(s, gx::KC_BUPDATE); K->bupdate(A, dt_cfl, s->U, s->E, s->U, &s->dscal->dtmin_bits, cfl_in_step, s->stream); }
+  }
+  rc = apply_boundaries(s, s->U, neq, 1, 0); if (rc) return rc;           // boundaryI :216
+  rc = apply_user_bc(s, s->U, 1); if (rc) return rc;
+  if (!cfl_in_step) {
+    LaunchScope ls(s, gx::KC_PRIM);
+    K->calcprim(A, s->U, nullptr, nullptr, &s->dscal->dtmin_bits, 1, s->stream);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return GX_OK;
+}
+
 static int tstep_enqueue(gx_solver* s, double dt_cfl) {
+  if (s->fused) return tstep_enqueue_fused(s, dt_cfl);
   const gx::KernelTable* K = s->K;
   const StepArgs& A = s->A;
   const int neq = A.g.neq;
@@ -588,11 +643,12 @@ int gx_get_state(gx_solver* s, double* u, double* primit, double* temp) {
   const Grid& g = s->A.g;
   int rc;
   if (u) { rc = download_aos(s, s->U, u, g.neq); if (rc) return rc; }
-  if (primit) { rc = download_aos(s, s->W, primit, g.neq); if (rc) return rc; }
-  if (temp) {
-    if (!s->Temp) { CUDA_TRY(cudaMalloc((void**)&s->Temp, (size_t)g.vs * sizeof(double))); CUDA_TRY(cudaMemsetAsync(s->Temp, 0, (size_t)g.vs * sizeof(double), s->stream)); }
-    { LaunchScope ls(s, gx::KC_PRIM); s->K->calcprim(s->A, s->U, s->W, s->Temp, nullptr, 0, s->stream); }
-    rc = download_aos(s, s->Temp, temp, 1); if (rc) return rc;
+  if (primit || temp) {                              // calcprim(u, primit) over the whole array, on demand
+    rc = ensure_array(s, &s->W, g.neq); if (rc) return rc;
+    if (temp) { rc = ensure_array(s, &s->Temp, 1); if (rc) return rc; }
+    { LaunchScope ls(s, gx::KC_PRIM); s->K->calcprim(s->A, s->U, s->W, temp ? s->Temp : nullptr, nullptr, 0, s->stream); }
+    if (primit) { rc = download_aos(s, s->W, primit, g.neq); if (rc) return rc; }
+    if (temp) { rc = download_aos(s, s->Temp, temp, 1); if (rc) return rc; }
   }
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   collect_timed(s);

@@ -55,9 +55,11 @@ __global__ void __launch_bounds__(128) k_calcprim(const StepArgs A, const double
     for (int q = 0; q < (MHD ? 8 : 5); ++q) u[q] = U[q * g.vs + c];
     const double pas0 = g.npas > 0 ? U[(long long)g.neqdyn * g.vs + c] : 0.0;
     gxp::u2prim<MHD>(A.phys, u, w, pas0, T);
+    if (W) {
 #pragma unroll
-    for (int q = 0; q < (MHD ? 8 : 5); ++q) W[q * g.vs + c] = w[q];
-    for (int q = g.neqdyn; q < g.neq; ++q) W[q * g.vs + c] = U[q * g.vs + c];
+      for (int q = 0; q < (MHD ? 8 : 5); ++q) W[q * g.vs + c] = w[q];
+      for (int q = g.neqdyn; q < g.neq; ++q) W[q * g.vs + c] = U[q * g.vs + c];
+    }
     if (Temp) Temp[c] = T;
     if (want_cfl && i >= 1 && i <= g.nx && j >= 1 && j <= g.ny && k >= 1 && k <= g.nz) {
       if (MHD) {
@@ -212,6 +214,39 @@ __global__ void __launch_bounds__(128) k_viscous(const StepArgs A, double eta, c
 }
 
 // ---------------------------------------------------------------------------
+// flux-CD evolution of B from the cell-centred E (flux_cd_update, src/flux_cd_module.f90:311-321),
+// the companion of the fused stage kernel; with want_cfl also the CFL candidates of the
+// finished state (get_timestep, src/hydro_core.f90:644-675).
+template <bool CFL>
+__global__ void __launch_bounds__(256) k_bupdate(const StepArgs A, double dt, const double* Ub, const double* __restrict__ E,
+                                                 double* dst, unsigned long long* dtmin_bits) {
+  const Grid& g = A.g;
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) + 1, j = (int)blockIdx.y + 1, k = (int)blockIdx.z + 1;
+  double dtp = 1.e30;
+  if (i <= g.nx) {
+    const long long c = g.idx(i, j, k), sy = g.px, sz = (long long)g.px * g.py, vs = g.vs;
+    const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
+    const double bx = Ub[5 * vs + c] - 0.5 * dtdy * (E[2 * vs + c + sy] - E[2 * vs + c - sy]) + 0.5 * dtdz * (E[1 * vs + c + sz] - E[1 * vs + c - sz]);
+    const double by = Ub[6 * vs + c] + 0.5 * dtdx * (E[2 * vs + c + 1] - E[2 * vs + c - 1]) - 0.5 * dtdz * (E[0 * vs + c + sz] - E[0 * vs + c - sz]);
+    const double bz = Ub[7 * vs + c] - 0.5 * dtdx * (E[1 * vs + c + 1] - E[1 * vs + c - 1]) + 0.5 * dtdy * (E[0 * vs + c + sy] - E[0 * vs + c - sy]);
+    dst[5 * vs + c] = bx; dst[6 * vs + c] = by; dst[7 * vs + c] = bz;
+    if (CFL) {
+      double u[8], w[8], T;
+#pragma unroll
+      for (int q = 0; q < 5; ++q) u[q] = dst[q * vs + c];
+      u[5] = bx; u[6] = by; u[7] = bz;
+      gxp::u2prim<true>(A.phys, u, w, 0.0, T);
+      double cx, cy, cz;
+      gxp::cfast3(A.phys, w[4], w[0], w[5], w[6], w[7], cx, cy, cz);
+      dtp = fmin(dtp, g.dx / (fabs(w[1]) + cx));
+      dtp = fmin(dtp, g.dy / (fabs(w[2]) + cy));
+      dtp = fmin(dtp, g.dz / (fabs(w[3]) + cz));
+    }
+  }
+  if (CFL) block_atomic_min(dtp, dtmin_bits);
+}
+
+// ---------------------------------------------------------------------------
 // launchers
 static inline dim3 grid_for(int nxr, int nyr, int nzr, int bx) { return dim3((unsigned)((nxr + bx - 1) / bx), (unsigned)nyr, (unsigned)nzr); }
 
@@ -273,7 +308,30 @@ static void l_viscous(const StepArgs& A, double eta, const double* UP, double* U
   k_viscous<<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(A, eta, UP, U);
 }
 
-static const KernelTable table = {l_calcprim, l_fluxes, l_efield, l_update, l_viscous};
+// fused stage kernels live in gx_stage.cu, one translation unit per solver
+int l_stage_1(const StepArgs&, int, double, const double*, const double*, double*, double*, int, unsigned long long*, int, int*, cudaStream_t);
+int l_stage_2(const StepArgs&, int, double, const double*, const double*, double*, double*, int, unsigned long long*, int, int*, cudaStream_t);
+int l_stage_3(const StepArgs&, int, double, const double*, const double*, double*, double*, int, unsigned long long*, int, int*, cudaStream_t);
+int l_stage_4(const StepArgs&, int, double, const double*, const double*, double*, double*, int, unsigned long long*, int, int*, cudaStream_t);
+static int l_stage(const StepArgs& A, int order, double dt, const double* S, const double* Ub, double* dst, double* E, int kz,
+                   unsigned long long* dtmin_bits, int want_cfl, int* errflag, cudaStream_t s) {
+  switch (A.solver) {
+    case GX_SOLVER_HLL:  return l_stage_1(A, order, dt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag, s);
+    case GX_SOLVER_HLLC: return l_stage_2(A, order, dt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag, s);
+    case GX_SOLVER_HLLE: return l_stage_3(A, order, dt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag, s);
+    case GX_SOLVER_HLLD: return l_stage_4(A, order, dt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag, s);
+  }
+  return GX_EUNSUPPORTED;
+}
+
+static void l_bupdate(const StepArgs& A, double dt, const double* Ub, const double* E, double* dst, unsigned long long* dtmin_bits, int want_cfl, cudaStream_t s) {
+  const Grid& g = A.g;
+  dim3 grid = grid_for(g.nx, g.ny, g.nz, 256);
+  if (want_cfl) k_bupdate<true><<<grid, 256, 0, s>>>(A, dt, Ub, E, dst, dtmin_bits);
+  else k_bupdate<false><<<grid, 256, 0, s>>>(A, dt, Ub, E, dst, dtmin_bits);
+}
+
+static const KernelTable table = {l_calcprim, l_fluxes, l_efield, l_update, l_viscous, l_stage, l_bupdate};
 
 }  // namespace GX_NS
 

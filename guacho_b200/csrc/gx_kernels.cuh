@@ -40,7 +40,7 @@ struct StepArgs {
 };
 
 // classes for the per-kernel timing table (gx_kernel_time_ms)
-enum { KC_FLUX = 0, KC_UPDATE = 1, KC_EFIELD = 2, KC_PRIM = 3, KC_BC = 4, KC_XPOSE = 5, KC_VISC = 6, KC_COUNT = 7 };
+enum { KC_FLUX = 0, KC_UPDATE = 1, KC_EFIELD = 2, KC_PRIM = 3, KC_BC = 4, KC_XPOSE = 5, KC_VISC = 6, KC_STAGE1 = 7, KC_STAGE2 = 8, KC_BUPDATE = 9, KC_COUNT = 10 };
 
 // One set of launchers per build flavour.
 struct KernelTable {
@@ -52,7 +52,21 @@ struct KernelTable {
   // dst = U - dt*div(F) [flux-CD for B] [+ dt*S(W)]
   void (*update)(const StepArgs&, double dt, const double* U, const double* F, const double* E, const double* W, double* dst, cudaStream_t);
   void (*viscous)(const StepArgs&, double eta, const double* UP, double* U, cudaStream_t);
+  // fused stage (gx_stage.cu): dst = Ub - dt*div F(prim(S)) for the non-B variables (all variables
+  // without flux-CD), E = cell-centred electric field of the same fluxes (flux-CD only);
+  // without flux-CD and with want_cfl the CFL minimum of the new state goes to *dtmin_bits.
+  int (*stage)(const StepArgs&, int order, double dt, const double* S, const double* Ub, double* dst, double* E, int kz,
+               unsigned long long* dtmin_bits, int want_cfl, int* errflag, cudaStream_t);
+  // flux-CD: dst(B) = Ub(B) - dt*curl E (central differences); want_cfl: CFL minimum of dst
+  void (*bupdate)(const StepArgs&, double dt, const double* Ub, const double* E, double* dst,
+                  unsigned long long* dtmin_bits, int want_cfl, cudaStream_t);
 };
+#ifndef GX_STAGE_TX
+#define GX_STAGE_TX 32
+#endif
+#ifndef GX_STAGE_TY
+#define GX_STAGE_TY 10
+#endif
 const KernelTable* kernels_strict();
 const KernelTable* kernels_fast();
 

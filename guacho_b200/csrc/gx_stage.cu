@@ -1,0 +1,343 @@
+// gx_stage.cu — fused stage kernel of the hydro/MHD step for sm_100a.
+//
+// One launch does what the reference does in five full-array passes per stage
+// (src/hydro_solver.f90:155-184): calcprim (u2prim, src/hydro_core.f90:46-129), the
+// hll?fluxes(choice) sweep in x, y and z (src/hlld.f90:331-432 and twins), get_efield
+// (src/flux_cd_module.f90:245-273) and the conservative update of step()
+// (src/hydro_solver.f90:99-107).  Primitives and face fluxes never touch HBM: the kernel
+// reads the conserved state once and writes the updated state (and, with flux-CD, the
+// cell-centred electric field) once.
+//
+// Structure (2.5-D marching, FP64 stencil):
+//   * a CTA owns a TX x TY = 32 x 10 column of cells and marches along z through KZ planes;
+//   * conserved planes are staged into shared memory with cp.async (LDGSTS, 8-byte
+//     elements: tile rows start on odd 8-byte offsets once the halo is included) one
+//     plane ahead of the compute, converted in place to primitives, and kept in a ring
+//     of 2*ORDER planes (the z stencil) + 1 in flight;
+//   * warp r (< TY) owns row r of the tile, lane l owns cell i0+l.  Each thread solves the
+//     LOWER x face and LOWER y face of its cell and the UPPER z face (whose flux is
+//     carried in registers to the next plane), so every interface is solved exactly once
+//     inside the tile; warp TY solves the tile's closing faces (the y faces above the
+//     last row, then the x faces right of the last column);
+//   * face fluxes are exchanged through shared memory and the update is written with
+//     fully coalesced 256-byte row segments.
+// Compiled per (flavour, solver): -DGX_FLAVOUR_STRICT|-DGX_FLAVOUR_FAST, -DGX_STAGE_SOLVER=n.
+#include "gx_kernels.cuh"
+
+#if defined(GX_FLAVOUR_STRICT)
+#define GX_NS strict_ns
+#elif defined(GX_FLAVOUR_FAST)
+#define GX_NS fast_ns
+#else
+#error "define GX_FLAVOUR_STRICT or GX_FLAVOUR_FAST"
+#endif
+#ifndef GX_STAGE_SOLVER
+#error "define GX_STAGE_SOLVER (1..4)"
+#endif
+
+namespace gx {
+namespace GX_NS {
+
+// storage component of rotated slot c for sweep direction D (swapy / swapz as an index map,
+// src/hydro_core.f90:485-534)
+template <int D> __device__ __forceinline__ constexpr int rot(int c) {
+  return (c == 1) ? 1 + D : (c == 1 + D) ? 1 : (c == 5) ? 5 + D : (c == 5 + D) ? 5 : c;
+}
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int NQ_, int ORDER_>
+struct StageGeom {
+  static constexpr int NQ = NQ_, H = ORDER_;
+  static constexpr int TX = GX_STAGE_TX, TY = GX_STAGE_TY;
+  static constexpr int NW = TY + 1, NT = NW * 32;
+  static constexpr int CX = TX + 2 * H;          // staged columns  i0-H .. i0+TX+H-1
+  static constexpr int RY = TY + 2 * H;          // staged rows     j0-H .. j0+TY+H-1
+  static constexpr int NSLOT = 2 * H + 1;        // z ring: 2H planes of stencil + 1 in flight
+  static constexpr int PCELLS = CX * RY;
+  static constexpr int PLANE = NQ * PCELLS;      // doubles per ring slot
+  static constexpr int XB = NQ * TY * (TX + 1);  // x-face flux exchange
+  static constexpr int YB = NQ * (TY + 1) * TX;  // y-face flux exchange
+  static constexpr int ZB = NQ * TY * TX;        // z-face flux hand-over (thread-private slots)
+  static constexpr size_t SMEM = sizeof(double) * ((size_t)NSLOT * PLANE + XB + YB + ZB);
+};
+
+// block-wide min of positive doubles -> one atomicMin on the ordered bit pattern
+template <int NT>
+__device__ __forceinline__ void stage_block_min(double v, unsigned long long* dst, double* scratch) {
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    v = lane < NT / 32 ? scratch[lane] : 1.e30;
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) atomicMin(dst, (unsigned long long)__double_as_longlong(v));
+  }
+}
+
+// One interface with a RUN-TIME sweep direction: the 2*ORDER states are gathered from the
+// staged primitive planes through per-direction variable offsets (swapy/swapz,
+// src/hydro_core.f90:485-534, as an index map), reconstructed (src/hydro_core.f90:712-798),
+// solved (prim2fhll*) and the flux is scattered back through the same map.  Keeping the
+// direction a run-time value means ONE copy of the solver in the instruction stream for
+// all x, y and z faces (the kernel is instruction-cache bound otherwise).
+//   o_m2..o_p1 : offsets (doubles, inside the ring) of variable 0 of cells  l-1, l | r, r+1
+//   vn,vt1,vt2 : offsets of the normal / transverse velocity components (bn.. = vn.. + 4 planes)
+struct FaceJob {
+  int o_m2, o_m1, o_p0, o_p1;      // ring offsets of the four cells
+  int vn, vt1, vt2;                // rotated velocity components, in doubles (component * PCELLS)
+  int out, ovs;                    // exchange-buffer offset of variable 0, variable stride
+  int on, ot1, ot2;                // rotated components of the output (component index)
+  bool store, check;
+};
+
+template <int SOLVER, int LIM, int ORDER, int NQ, int PC>
+__device__ __forceinline__ int solve_job(const gxp::Phys& P, const double* ring, double* xch, const FaceJob& J) {
+  double wl[8], wr[8], fr[8];
+  {
+    const int off[8] = {0, J.vn, J.vt1, J.vt2, 4 * PC, J.vn + 4 * PC, J.vt1 + 4 * PC, J.vt2 + 4 * PC};
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      double pl = ring[J.o_m1 + off[q]], pr = ring[J.o_p0 + off[q]];
+      if (ORDER == 2) gxp::reconstruct<LIM>(ring[J.o_m2 + off[q]], pl, pr, ring[J.o_p1 + off[q]]);
+      wl[q] = pl; wr[q] = pr;
+    }
+  }
+  gxp::PasInfo I;
+  const int err = gxp::riemann<SOLVER>(P, wl, wr, fr, I);
+  if (J.store) {
+    double* o = xch + J.out;
+    const int oc[8] = {0, J.on, J.ot1, J.ot2, 4, J.on + 4, J.ot1 + 4, J.ot2 + 4};
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) o[oc[q] * J.ovs] = fr[q];
+  }
+  return J.check ? err : 0;
+}
+
+template <int SOLVER, int LIM, int ORDER, bool FLUXCD>
+__global__ void __launch_bounds__(StageGeom<(SOLVER == GX_SOLVER_HLLE || SOLVER == GX_SOLVER_HLLD) ? 8 : 5, ORDER>::NT, 1)
+k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const double* Ub, double* dst,
+        double* __restrict__ E, const int kz, unsigned long long* dtmin_bits, const int want_cfl, int* errflag) {
+  constexpr bool MHD = (SOLVER == GX_SOLVER_HLLE || SOLVER == GX_SOLVER_HLLD);
+  constexpr int NQ = MHD ? 8 : 5;
+  using G = StageGeom<NQ, ORDER>;
+  constexpr int H = G::H, TX = G::TX, TY = G::TY, CX = G::CX, NSLOT = G::NSLOT, NT = G::NT;
+  constexpr int PC = G::PCELLS;
+  constexpr int XBV = TY * (TX + 1), YBV = (TY + 1) * TX, ZBV = TY * TX;
+  extern __shared__ double sm[];
+  double* const ring = sm;
+  double* const xch = sm + (size_t)NSLOT * G::PLANE;     // exchange buffers: x | y | z
+  constexpr int XB0 = 0, YB0 = G::XB, ZB0 = G::XB + G::YB;
+  const double* const xb = xch + XB0;                    // [q][TY][TX+1]
+  const double* const yb = xch + YB0;                    // [q][TY+1][TX]
+  const double* const zb = xch + ZB0;                    // [q][TY][TX]
+
+  const Grid& g = A.g;
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int i0 = 1 + (int)blockIdx.x * TX, j0 = 1 + (int)blockIdx.y * TY, k0 = 1 + (int)blockIdx.z * kz;
+  const int kend = min(k0 + kz - 1, g.nz);
+  const long long vs = g.vs;
+
+  // ---- plane staging: conserved -> shared (cp.async), converted in place to primitives ----
+  auto slot_off = [&](int p) { return ((p - (k0 - H)) % NSLOT) * G::PLANE; };
+  auto issue_load = [&](int p) {
+    double* sl = ring + slot_off(p);
+    const int kk = min(p, g.nz + 2);
+    for (int c = tid; c < PC; c += NT) {
+      const int rr = c / CX, cc = c - rr * CX;
+      const int i = min(i0 - H + cc, g.nx + 2), j = min(j0 - H + rr, g.ny + 2);
+      const double* src = S + g.idx(i, j, kk);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) cp_async8(sl + q * PC + c, src + q * vs);
+    }
+    cp_async_commit();
+  };
+  auto convert = [&](int p) {      // each thread converts exactly the cells it staged itself
+    double* sl = ring + slot_off(p);
+    for (int c = tid; c < PC; c += NT) {
+      double u[8], w[8], T;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) u[q] = sl[q * PC + c];
+      gxp::u2prim<MHD>(A.phys, u, w, 0.0, T);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) sl[q * PC + c] = w[q];
+    }
+  };
+
+  for (int p = k0 - H; p <= k0 + H - 1; ++p) issue_load(p);
+  cp_async_wait_all();
+  for (int p = k0 - H; p <= k0 + H - 1; ++p) convert(p);
+  __syncthreads();
+
+  const bool main_warp = wrp < TY;
+  const int i = i0 + lane, j = j0 + wrp;
+  const bool cell_ok = main_warp && i <= g.nx && j <= g.ny;
+  const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
+  const int cidx = (wrp + H) * CX + (lane + H);          // this thread's cell inside a staged plane
+  double hprev[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) hprev[q] = 0.0;
+  double dtp = 1.e30;
+  int err = 0;
+
+  for (int k = k0 - 1; k <= kend; ++k) {
+    if (k < kend) issue_load(k + H + 1);                  // lands in the slot of plane k-H (free since the last barrier)
+    const int sk = slot_off(k);
+    // jobs of this thread: main warps solve the lower x face, the lower y face and the upper z face
+    // of their cell; warp TY closes the tile (y faces above the last row, x faces right of the last column)
+    const int njobs = main_warp ? 3 : 2;
+    double ub[8];
+    const long long cg = g.idx(min(i, g.nx), min(j, g.ny), max(k, 1));
+#pragma unroll 1
+    for (int jb = (k >= k0 ? 0 : 2); jb < njobs; ++jb) {
+      FaceJob J;
+      if (main_warp) {
+        if (jb == 0) {                                    // lower x face of (i,j,k)
+          const int c = sk + cidx;
+          J.o_m2 = c - 2; J.o_m1 = c - 1; J.o_p0 = c; J.o_p1 = c + 1;
+          J.on = 1; J.ot1 = 2; J.ot2 = 3;
+          J.out = XB0 + wrp * (TX + 1) + lane; J.ovs = XBV;
+          J.store = true; J.check = (i <= g.nx + 1 && j <= g.ny);
+        } else if (jb == 1) {                             // lower y face
+          const int c = sk + cidx;
+          J.o_m2 = c - 2 * CX; J.o_m1 = c - CX; J.o_p0 = c; J.o_p1 = c + CX;
+          J.on = 2; J.ot1 = 1; J.ot2 = 3;
+          J.out = YB0 + wrp * TX + lane; J.ovs = YBV;
+          J.store = true; J.check = (i <= g.nx && j <= g.ny + 1);
+        } else {                                          // upper z face: planes k-H+1 .. k+H
+          J.o_m1 = sk + cidx; J.o_p0 = slot_off(k + 1) + cidx;
+          J.o_m2 = (ORDER == 2) ? slot_off(k - 1) + cidx : J.o_m1;
+          J.o_p1 = (ORDER == 2) ? slot_off(k + 2) + cidx : J.o_p0;
+          J.on = 3; J.ot1 = 2; J.ot2 = 1;
+          J.out = ZB0 + wrp * TX + lane; J.ovs = ZBV;
+          J.store = true; J.check = cell_ok;
+          if (k >= k0) {                                  // base state for the update: in flight during the z solve
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) if (!(FLUXCD && q >= 5)) ub[q] = Ub[q * vs + cg];
+          }
+        }
+      } else {
+        if (jb == 0) {                                    // y faces above the last row of the tile
+          const int c = sk + (TY + H) * CX + (lane + H);
+          J.o_m2 = c - 2 * CX; J.o_m1 = c - CX; J.o_p0 = c; J.o_p1 = c + CX;
+          J.on = 2; J.ot1 = 1; J.ot2 = 3;
+          J.out = YB0 + TY * TX + lane; J.ovs = YBV;
+          J.store = true; J.check = (i <= g.nx && j0 + TY <= g.ny + 1);
+        } else {                                          // x faces right of the last column: row = lane
+          const int row = min(lane, TY - 1);
+          const int c = sk + (row + H) * CX + (TX + H);
+          J.o_m2 = c - 2; J.o_m1 = c - 1; J.o_p0 = c; J.o_p1 = c + 1;
+          J.on = 1; J.ot1 = 2; J.ot2 = 3;
+          J.out = XB0 + row * (TX + 1) + TX; J.ovs = XBV;
+          J.store = lane < TY; J.check = (lane < TY && i0 + TX <= g.nx + 1 && j0 + lane <= g.ny);
+        }
+      }
+      J.vn = J.on * PC; J.vt1 = J.ot1 * PC; J.vt2 = J.ot2 * PC;
+      err |= solve_job<SOLVER, LIM, ORDER, NQ, PC>(A.phys, ring, xch, J);
+    }
+    __syncthreads();                                      // face fluxes visible
+    double h[8];
+    if (main_warp) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) h[q] = zb[q * ZBV + wrp * TX + lane];
+    }
+    if (k >= k0 && cell_ok) {
+      const long long c = g.idx(i, j, k);
+      double un[8];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        if (FLUXCD && q >= 5) continue;                   // B is advanced from E by k_bupdate
+        const double flo = xb[q * XBV + wrp * (TX + 1) + lane], fup = xb[q * XBV + wrp * (TX + 1) + lane + 1];
+        const double glo = yb[q * YBV + wrp * TX + lane], gup = yb[q * YBV + (wrp + 1) * TX + lane];
+        // step(): up = u - dt/dx (f(i)-f(i-1)) - dt/dy (g(j)-g(j-1)) - dt/dz (h(k)-h(k-1))   hydro_solver.f90:105-107
+        const double v = ub[q] - dtdx * (fup - flo) - dtdy * (gup - glo) - dtdz * (h[q] - hprev[q]);
+        un[q] = v;
+        dst[q * vs + c] = v;
+      }
+      if (FLUXCD) {                                       // get_efield, flux_cd_module.f90:258-265
+        const double f6l = xb[6 * XBV + wrp * (TX + 1) + lane], f6u = xb[6 * XBV + wrp * (TX + 1) + lane + 1];
+        const double f7l = xb[7 * XBV + wrp * (TX + 1) + lane], f7u = xb[7 * XBV + wrp * (TX + 1) + lane + 1];
+        const double g5l = yb[5 * YBV + wrp * TX + lane], g5u = yb[5 * YBV + (wrp + 1) * TX + lane];
+        const double g7l = yb[7 * YBV + wrp * TX + lane], g7u = yb[7 * YBV + (wrp + 1) * TX + lane];
+        E[0 * vs + c] = 0.25 * (-g7l - g7u + hprev[6] + h[6]);
+        E[1 * vs + c] = 0.25 * (+f7l + f7u - hprev[5] - h[5]);
+        E[2 * vs + c] = 0.25 * (-f6l - f6u + g5l + g5u);
+      } else if (want_cfl) {                              // get_timestep candidates of the new state, hydro_core.f90:644-675
+        double w[8], T;
+        gxp::u2prim<MHD>(A.phys, un, w, 0.0, T);
+        if (MHD) {
+          double cx, cy, cz;
+          gxp::cfast3(A.phys, w[4], w[0], w[5], w[6], w[7], cx, cy, cz);
+          dtp = fmin(dtp, g.dx / (fabs(w[1]) + cx));
+          dtp = fmin(dtp, g.dy / (fabs(w[2]) + cy));
+          dtp = fmin(dtp, g.dz / (fabs(w[3]) + cz));
+        } else {
+          const double cs = gxp::csound(A.phys, w[4], w[0]);
+          dtp = fmin(dtp, g.dx / (fabs(w[1]) + cs));
+          dtp = fmin(dtp, g.dy / (fabs(w[2]) + cs));
+          dtp = fmin(dtp, g.dz / (fabs(w[3]) + cs));
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) hprev[q] = h[q];
+    if (k < kend) { cp_async_wait_all(); convert(k + H + 1); }
+    __syncthreads();                                      // next plane ready; exchange buffers free
+  }
+  if (err) atomicOr(errflag, 1);
+  if (!FLUXCD && want_cfl) stage_block_min<NT>(dtp, dtmin_bits, xch);
+}
+
+// ---------------------------------------------------------------------------
+template <int SOLVER, int LIM, int ORDER, bool FLUXCD>
+static int launch_one(const StepArgs& A, double dt, const double* S, const double* Ub, double* dst, double* E, int kz,
+                      unsigned long long* dtmin_bits, int want_cfl, int* errflag, cudaStream_t st) {
+  constexpr bool MHD = (SOLVER == GX_SOLVER_HLLE || SOLVER == GX_SOLVER_HLLD);
+  using G = StageGeom<MHD ? 8 : 5, ORDER>;
+  auto kern = k_stage<SOLVER, LIM, ORDER, FLUXCD>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM) != cudaSuccess) return GX_ECUDA;
+  const Grid& g = A.g;
+  dim3 grid((g.nx + G::TX - 1) / G::TX, (g.ny + G::TY - 1) / G::TY, (g.nz + kz - 1) / kz);
+  kern<<<grid, G::NT, G::SMEM, st>>>(A, dt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag);
+  return GX_OK;
+}
+
+template <int SOLVER, int LIM, int ORDER>
+static int launch_cd(const StepArgs& A, double dt, const double* S, const double* Ub, double* dst, double* E, int kz,
+                     unsigned long long* dtmin_bits, int want_cfl, int* errflag, cudaStream_t st) {
+  constexpr bool MHD = (SOLVER == GX_SOLVER_HLLE || SOLVER == GX_SOLVER_HLLD);
+  if (MHD && A.flux_cd) return launch_one<SOLVER, LIM, ORDER, MHD>(A, dt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag, st);
+  return launch_one<SOLVER, LIM, ORDER, false>(A, dt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag, st);
+}
+
+#define GX_CAT2(a, b) a##b
+#define GX_CAT(a, b) GX_CAT2(a, b)
+// exported per (flavour, solver): l_stage_<solver>
+int GX_CAT(l_stage_, GX_STAGE_SOLVER)(const StepArgs& A, int order, double dt, const double* S, const double* Ub, double* dst,
+                                      double* E, int kz, unsigned long long* dtmin_bits, int want_cfl, int* errflag, cudaStream_t st) {
+  constexpr int SV = GX_STAGE_SOLVER;
+  if (order == 1) return launch_cd<SV, GX_LIMITER_NO_AVERAGE, 1>(A, dt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag, st);
+  switch (A.limiter) {
+#ifndef GX_DEV_MINMOD_ONLY
+    case GX_LIMITER_NO_AVERAGE: return launch_cd<SV, GX_LIMITER_NO_AVERAGE, 2>(A, dt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag, st);
+    case GX_LIMITER_NO_LIMIT:   return launch_cd<SV, GX_LIMITER_NO_LIMIT, 2>(A, dt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag, st);
+    case GX_LIMITER_VAN_LEER:   return launch_cd<SV, GX_LIMITER_VAN_LEER, 2>(A, dt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag, st);
+    case GX_LIMITER_VAN_ALBADA: return launch_cd<SV, GX_LIMITER_VAN_ALBADA, 2>(A, dt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag, st);
+    case GX_LIMITER_UMIST:      return launch_cd<SV, GX_LIMITER_UMIST, 2>(A, dt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag, st);
+    case GX_LIMITER_WOODWARD:   return launch_cd<SV, GX_LIMITER_WOODWARD, 2>(A, dt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag, st);
+    case GX_LIMITER_SUPERBEE:   return launch_cd<SV, GX_LIMITER_SUPERBEE, 2>(A, dt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag, st);
+#endif
+    case GX_LIMITER_MINMOD:     return launch_cd<SV, GX_LIMITER_MINMOD, 2>(A, dt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag, st);
+  }
+  return GX_EUNSUPPORTED;
+}
+
+}  // namespace GX_NS
+}  // namespace gx

@@ -26,7 +26,7 @@ EXPORTS = (
     "gx_kernel_time_ms", "gx_set_profiling", "gx_build_info",
 )
 
-KERNEL_CLASSES = ("flux", "update", "efield", "prim", "bc", "xpose", "visc")
+KERNEL_CLASSES = ("flux", "update", "efield", "prim", "bc", "xpose", "visc", "stage1", "stage2", "bupdate")
 
 
 class GxError(RuntimeError):
