@@ -74,6 +74,7 @@ struct gx_solver {
   struct DevScalars { unsigned long long dtmin_bits; int err; int pad; }* dscal = nullptr;   // device
   DevScalars* hscal = nullptr;                                // pinned host mirror
   bool have_state = false;
+  bool ghosts_stale = false;   // self-periodic ghost layers of u/up not materialised since the last fused step
   bool fused = false;      // fused stage kernels (gx_stage.cu); otherwise the pass-per-routine kernels
   int kz = 16;             // planes one CTA of the fused stage kernel marches through
   double time = 0.0;
@@ -303,9 +304,10 @@ static void launch_bc_face(gx_solver* s, double* A, int nvar, int dir, int side,
 // kind 0: conserved/primitive array (closed wall flips normal momentum, boundaries.f90:146-199, 361-438)
 // kind 1: electric field (closed wall flips e(1) on x walls, e(2) on y walls, nothing on z walls,
 //         flux_cd_module.f90:143-192)
-static int apply_boundaries(gx_solver* s, double* A, int nvar, int nl, int kind) {
+static int apply_boundaries(gx_solver* s, double* A, int nvar, int nl, int kind, bool skip_wrapped = false) {
   for (int dir = 0; dir < 3; ++dir) {
     if (s->nb[dir] == 1 && s->periodic[dir]) {            // neighbour is the block itself
+      if (skip_wrapped && s->A.wrap[dir]) continue;       // the fused kernels wrap their reads instead
       launch_bc_face(s, A, nvar, dir, 0, 0, nl, -1);
       launch_bc_face(s, A, nvar, dir, 1, 0, nl, -1);
     } else {
@@ -397,7 +399,7 @@ int gx_create(const gx_config* c, gx_solver** out) {
   g.cx = c->cx; g.cy = c->cy; g.cz = c->cz;
   g.nxtot = c->nxtot; g.nytot = c->nytot; g.nztot = c->nztot;
   g.dx = c->dx; g.dy = c->dy; g.dz = c->dz;
-  s->A.phys.cv = c->cv; s->A.phys.gamma = c->gamma; s->A.phys.Tempsc = c->Tempsc;
+  s->A.phys.cv = c->cv; s->A.phys.gamma = c->gamma; s->A.phys.Tempsc = c->Tempsc; s->A.phys.inv_cv = 1.0 / c->cv;
   s->A.phys.eos = c->eq_of_state; s->A.phys.neqdyn = c->neqdyn; s->A.phys.npas = c->npas;
   s->A.solver = c->riemann_solver; s->A.limiter = c->slope_limiter;
   s->A.flux_cd = c->enable_flux_cd; s->A.eight_wave = c->eight_wave; s->A.user_src = c->user_source_terms;
@@ -423,7 +425,25 @@ int gx_create(const gx_config* c, gx_solver** out) {
   // fused stage kernels cover the dynamic variables; passives, the 8-wave / user sources and
   // eta != 0 (viscous_copy needs up's stale half-step ghosts) take the pass-per-routine kernels
   s->fused = c->npas == 0 && !c->eight_wave && !c->user_source_terms && c->eta == 0.0 && !getenv("GX_NO_FUSED");
+  {
+    // planes per CTA of the fused stage kernel: as long as possible (the z prologue costs 2*ORDER
+    // plane loads and one extra z solve per chunk) while the grid still fills whole waves of SMs
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+    const long long tiles = (long long)((nx + GX_STAGE_TX - 1) / GX_STAGE_TX) * ((ny + GX_STAGE_TY - 1) / GX_STAGE_TY);
+    int best_kz = nz; double best_eff = -1.0;
+    for (int chunks = 1; chunks <= nz; ++chunks) {
+      const int kzc = (nz + chunks - 1) / chunks;
+      const long long total = tiles * ((nz + kzc - 1) / kzc);
+      const double eff = (double)total / (double)(((total + sms - 1) / sms) * sms);
+      if (eff > best_eff + 1e-9) { best_eff = eff; best_kz = kzc; }
+      if (eff >= 0.95 && total >= 2LL * sms) { best_kz = kzc; break; }
+      if (kzc <= 4) break;
+    }
+    s->kz = best_kz;
+  }
   if (const char* e = getenv("GX_KZ")) s->kz = std::max(1, atoi(e));
+  // a user boundary functor may write ghost cells, so ghosts must be real arrays then
+  for (int d = 0; d < 3; ++d) s->A.wrap[d] = (s->fused && s->periodic[d] && s->nb[d] == 1 && !c->bc_user && !getenv("GX_NO_WRAP")) ? 1 : 0;
   ALLOC(s->U, var_bytes * g.neq);
   ALLOC(s->UP, var_bytes * g.neq);
   if (!s->fused) {                                   // primitives and face fluxes only exist in HBM on the unfused path
@@ -511,6 +531,7 @@ int gx_set_state(gx_solver* s, const double* u) {
   rc = finish_u(s); if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   collect_timed(s);
+  s->ghosts_stale = false;
   s->have_state = true;
   return GX_OK;
 }
@@ -549,23 +570,24 @@ static int tstep_enqueue_fused(gx_solver* s, double dt_cfl) {
   int rc;
   { LaunchScope ls(s, gx::KC_STAGE1); rc = K->stage(A, 1, dtm, s->U, s->U, s->UP, s->E, s->kz, nullptr, 0, &s->dscal->err, s->stream); } if (rc) return fail(rc, "stage-1 launch");
   if (A.flux_cd) {
-    rc = apply_boundaries(s, s->E, 3, 1, 1); if (rc) return rc;
+    rc = apply_boundaries(s, s->E, 3, 1, 1, true); if (rc) return rc;
     { LaunchScope ls(s, gx::KC_BUPDATE); K->bupdate(A, dtm, s->U, s->E, s->UP, nullptr, 0, s->stream); }
   }
-  rc = apply_boundaries(s, s->UP, neq, 2, 0); if (rc) return rc;          // boundaryII :169
+  rc = apply_boundaries(s, s->UP, neq, 2, 0, true); if (rc) return rc;          // boundaryII :169
   rc = apply_user_bc(s, s->UP, 2); if (rc) return rc;
   rc = reset_dtmin(s); if (rc) return rc;
   { LaunchScope ls(s, gx::KC_STAGE2); rc = K->stage(A, 2, dt_cfl, s->UP, s->U, s->U, s->E, s->kz, &s->dscal->dtmin_bits, cfl_in_step && !A.flux_cd, &s->dscal->err, s->stream); } if (rc) return fail(rc, "stage-2 launch");
   if (A.flux_cd) {
-    rc = apply_boundaries(s, s->E, 3, 1, 1); if (rc) return rc;
+    rc = apply_boundaries(s, s->E, 3, 1, 1, true); if (rc) return rc;
     { LaunchScope ls(s, gx::KC_BUPDATE); K->bupdate(A, dt_cfl, s->U, s->E, s->U, &s->dscal->dtmin_bits, cfl_in_step, s->stream); }
   }
-  rc = apply_boundaries(s, s->U, neq, 1, 0); if (rc) return rc;           // boundaryI :216
+  rc = apply_boundaries(s, s->U, neq, 1, 0, true); if (rc) return rc;           // boundaryI :216
   rc = apply_user_bc(s, s->U, 1); if (rc) return rc;
   if (!cfl_in_step) {
     LaunchScope ls(s, gx::KC_PRIM);
     K->calcprim(A, s->U, nullptr, nullptr, &s->dscal->dtmin_bits, 1, s->stream);
   }
+  s->ghosts_stale = s->A.wrap[0] || s->A.wrap[1] || s->A.wrap[2];
   CUDA_TRY(cudaGetLastError());
   return GX_OK;
 }
@@ -642,6 +664,11 @@ int gx_get_state(gx_solver* s, double* u, double* primit, double* temp) {
   cudaSetDevice(s->device);
   const Grid& g = s->A.g;
   int rc;
+  if (s->ghosts_stale) {                              // boundaryI / boundaryII copies the fused step did not need
+    rc = apply_boundaries(s, s->U, g.neq, 1, 0); if (rc) return rc;
+    rc = apply_boundaries(s, s->UP, g.neq, 2, 0); if (rc) return rc;
+    s->ghosts_stale = false;
+  }
   if (u) { rc = download_aos(s, s->U, u, g.neq); if (rc) return rc; }
   if (primit || temp) {                              // calcprim(u, primit) over the whole array, on demand
     rc = ensure_array(s, &s->W, g.neq); if (rc) return rc;
@@ -658,7 +685,13 @@ int gx_get_state(gx_solver* s, double* u, double* primit, double* temp) {
 int gx_get_up(gx_solver* s, double* up) {
   if (!s || !up) return fail(GX_EINVAL, "null argument");
   cudaSetDevice(s->device);
-  int rc = download_aos(s, s->UP, up, s->A.g.neq); if (rc) return rc;
+  int rc;
+  if (s->ghosts_stale) {
+    rc = apply_boundaries(s, s->U, s->A.g.neq, 1, 0); if (rc) return rc;
+    rc = apply_boundaries(s, s->UP, s->A.g.neq, 2, 0); if (rc) return rc;
+    s->ghosts_stale = false;
+  }
+  rc = download_aos(s, s->UP, up, s->A.g.neq); if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   return GX_OK;
 }

@@ -226,9 +226,13 @@ __global__ void __launch_bounds__(256) k_bupdate(const StepArgs A, double dt, co
   if (i <= g.nx) {
     const long long c = g.idx(i, j, k), sy = g.px, sz = (long long)g.px * g.py, vs = g.vs;
     const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
-    const double bx = Ub[5 * vs + c] - 0.5 * dtdy * (E[2 * vs + c + sy] - E[2 * vs + c - sy]) + 0.5 * dtdz * (E[1 * vs + c + sz] - E[1 * vs + c - sz]);
-    const double by = Ub[6 * vs + c] + 0.5 * dtdx * (E[2 * vs + c + 1] - E[2 * vs + c - 1]) - 0.5 * dtdz * (E[0 * vs + c + sz] - E[0 * vs + c - sz]);
-    const double bz = Ub[7 * vs + c] - 0.5 * dtdx * (E[1 * vs + c + 1] - E[1 * vs + c - 1]) + 0.5 * dtdy * (E[0 * vs + c + sy] - E[0 * vs + c - sy]);
+    // neighbours of the E stencil; a self-periodic direction wraps instead of reading a ghost cell
+    const long long xm = (A.wrap[0] && i == 1) ? c + (g.nx - 1) : c - 1, xp = (A.wrap[0] && i == g.nx) ? c - (g.nx - 1) : c + 1;
+    const long long ym = (A.wrap[1] && j == 1) ? c + (g.ny - 1) * sy : c - sy, yp = (A.wrap[1] && j == g.ny) ? c - (g.ny - 1) * sy : c + sy;
+    const long long zm = (A.wrap[2] && k == 1) ? c + (g.nz - 1) * sz : c - sz, zp = (A.wrap[2] && k == g.nz) ? c - (g.nz - 1) * sz : c + sz;
+    const double bx = Ub[5 * vs + c] - 0.5 * dtdy * (E[2 * vs + yp] - E[2 * vs + ym]) + 0.5 * dtdz * (E[1 * vs + zp] - E[1 * vs + zm]);
+    const double by = Ub[6 * vs + c] + 0.5 * dtdx * (E[2 * vs + xp] - E[2 * vs + xm]) - 0.5 * dtdz * (E[0 * vs + zp] - E[0 * vs + zm]);
+    const double bz = Ub[7 * vs + c] - 0.5 * dtdx * (E[1 * vs + xp] - E[1 * vs + xm]) + 0.5 * dtdy * (E[0 * vs + yp] - E[0 * vs + ym]);
     dst[5 * vs + c] = bx; dst[6 * vs + c] = by; dst[7 * vs + c] = bz;
     if (CFL) {
       double u[8], w[8], T;

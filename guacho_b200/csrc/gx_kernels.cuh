@@ -33,6 +33,9 @@ struct GravityPoints {     // get_user_source_terms functor (EXO/user_mod.f90:15
 
 struct StepArgs {
   Grid g;
+  int wrap[3];             // direction is periodic with the block as its own neighbour: the fused
+                           // kernels read the wrapped cell instead of a ghost cell (ghosts are
+                           // then only materialised when the host asks for the arrays)
   gxp::Phys phys;
   int solver, limiter;
   int flux_cd, eight_wave, user_src;
@@ -65,7 +68,7 @@ struct KernelTable {
 #define GX_STAGE_TX 32
 #endif
 #ifndef GX_STAGE_TY
-#define GX_STAGE_TY 10
+#define GX_STAGE_TY 7
 #endif
 const KernelTable* kernels_strict();
 const KernelTable* kernels_fast();

@@ -16,11 +16,23 @@ namespace gxp {
 
 struct Phys {            // the scalar `parameter`s the cell routines read
   double cv, gamma, Tempsc;
+  double inv_cv;         // 1/cv (fast build: p = (...)*inv_cv instead of an IEEE division)
   int eos;               // GX_EOS_*
   int neqdyn, npas;      // neq = neqdyn + npas
 };
 
 __device__ __forceinline__ double sign1(double x) { return copysign(1.0, x); }   // Fortran sign(1.,x)
+
+// max / min policy.  fmax/fmin expand to DSETP + selects + NaN quieting + register moves
+// (~6 issue slots each on sm_100a); the fast build uses a bare compare-and-select (3 slots).
+// NaNs never reach these in a live run (the reference stops on NaN, hlld.f90:316-317).
+#if defined(GX_FLAVOUR_FAST)
+__device__ __forceinline__ double gx_max(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double gx_min(double a, double b) { return a < b ? a : b; }
+#else
+__device__ __forceinline__ double gx_max(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ double gx_min(double a, double b) { return fmin(a, b); }
+#endif
 
 // ---- division / square root policy ----
 // strict build (GX_FLAVOUR_STRICT, -fmad=false): IEEE a/b and sqrt, one per occurrence in the
@@ -37,21 +49,29 @@ __device__ __forceinline__ double fast_rcp(double x) {
   double t = fma(e, e, e);                                    // e + e^2
   return fma(r, t, r);                                        // error ~ e^3 = 2^-69
 }
-// s = sqrt(x), rs = 1/sqrt(x) for x > 0 (x == 0 -> s = 0, rs = inf-like large is never used)
+// s = sqrt(x), rs = 1/sqrt(x) for x > 0 (callers guarantee x > 0: densities, or a discriminant
+// clamped to a tiny positive number).  MUFU.RSQ64H seed (2^-22) + two coupled Newton steps.
 __device__ __forceinline__ void fast_sqrt_rsqrt(double x, double& s, double& rs) {
   double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));    // rel. error <= 2^-22
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double g = x * y, h = 0.5 * y;
   double r = fma(-h, g, 0.5);
   g = fma(g, r, g); h = fma(h, r, h);
   r = fma(-h, g, 0.5);
-  g = fma(g, r, g); h = fma(h, r, h);
-  s = (x > 0.0) ? g : ((x == 0.0) ? 0.0 : g);
-  rs = h + h;
+  s = fma(g, r, g);
+  rs = 2.0 * fma(h, r, h);
 }
-__device__ __forceinline__ double gx_sqrt(double x) { double s, rs; fast_sqrt_rsqrt(x, s, rs); return s; }
-// discriminant of the fast-speed formula: >= 0 analytically, may round to -eps with re-associated arithmetic
-__device__ __forceinline__ double gx_sqrt_disc(double x) { return gx_sqrt(fmax(x, 0.0)); }
+__device__ __forceinline__ double gx_sqrt(double x) {     // sqrt only: the last step needs no updated h
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x * y, h = 0.5 * y;
+  double r = fma(-h, g, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-h, g, 0.5);
+  return fma(g, r, g);
+}
+// discriminant of the fast-speed formula: >= 0 analytically, may round to -eps (or be exactly 0)
+__device__ __forceinline__ double gx_sqrt_disc(double x) { return gx_sqrt(gx_max(x, 1e-300)); }
 struct Den {                      // a denominator used one or more times
   double inv;
   __device__ __forceinline__ explicit Den(double b) : inv(fast_rcp(b)) {}
@@ -81,9 +101,9 @@ __device__ __forceinline__ double sqrt_prod(const SqrtDen&, const SqrtDen&, doub
 
 // ---- u2prim: src/hydro_core.f90:46-129 (dynamic variables only; passives are copies) ----
 // `pas0` is the first passive (needed by EOS_H_RATE only).
-template <bool MHD>
+template <bool MHD, bool WANT_T = true>
 __device__ __forceinline__ void u2prim(const Phys& P, const double (&u)[8], double (&w)[8], double pas0, double& T) {
-  double r = fmax(u[0], 1e-15);
+  double r = gx_max(u[0], 1e-15);
   w[0] = r;
   const Den dr(r);
   w[1] = dr.div(u[1]);
@@ -91,20 +111,25 @@ __device__ __forceinline__ void u2prim(const Phys& P, const double (&u)[8], doub
   w[3] = dr.div(u[3]);
   double ek = 0.5 * r * (w[1] * w[1] + w[2] * w[2] + w[3] * w[3]);
   double p;
+#if defined(GX_FLAVOUR_FAST)
+  if (MHD) p = (u[4] - ek - 0.5 * (u[5] * u[5] + u[6] * u[6] + u[7] * u[7])) * P.inv_cv;
+  else p = (u[4] - ek) * P.inv_cv;
+#else
   if (MHD) p = (u[4] - ek - 0.5 * (u[5] * u[5] + u[6] * u[6] + u[7] * u[7])) / P.cv;
   else p = (u[4] - ek) / P.cv;
-  p = fmax(p, 1e-16);
+#endif
+  p = gx_max(p, 1e-16);
   if (MHD) { w[5] = u[5]; w[6] = u[6]; w[7] = u[7]; }
   T = 0.0;
   if (P.eos == GX_EOS_ADIABATIC) {
-    T = (p / r) * P.Tempsc;
+    if (WANT_T) T = (p / r) * P.Tempsc;
   } else if (P.eos == GX_EOS_SINGLE_SPECIE) {
-    double rr = fmax(r, 1e-15);
-    T = fmax(1.0, (p / rr) * P.Tempsc);
+    double rr = gx_max(r, 1e-15);
+    T = gx_max(1.0, (p / rr) * P.Tempsc);
     p = rr * T / P.Tempsc;
   } else if (P.eos == GX_EOS_H_RATE && P.npas > 0) {
-    double dentot = fmax(2.0 * r - pas0, 1e-15);
-    T = fmax(1.0, (p / dentot) * P.Tempsc);
+    double dentot = gx_max(2.0 * r - pas0, 1e-15);
+    T = gx_max(1.0, (p / dentot) * P.Tempsc);
     p = dentot * T / P.Tempsc;
   }
   w[4] = p;
@@ -176,8 +201,15 @@ __device__ __forceinline__ double average(double a, double b) {
   if (LIM == GX_LIMITER_NO_AVERAGE) return 0.;
   if (LIM == GX_LIMITER_NO_LIMIT) return 0.5 * (a + b);
   if (LIM == GX_LIMITER_MINMOD) {
+#if defined(GX_FLAVOUR_FAST)
+    // same value as the reference expression (exactly a, b or 0), selected instead of computed:
+    // one FP64 compare + integer sign test instead of 4 FP64 ops and two fmin/fmax expansions
+    const double m = (fabs(a) < fabs(b)) ? a : b;
+    return ((__double2hiint(a) ^ __double2hiint(b)) >= 0) ? m : 0.0;
+#else
     double s = sign1(a);
-    return s * fmax(0., fmin(fabs(a), s * b));
+    return s * gx_max(0., gx_min(fabs(a), s * b));
+#endif
   }
   if (LIM == GX_LIMITER_VAN_LEER) {
     if (a * b <= 0.) return 0.;
@@ -191,20 +223,20 @@ __device__ __forceinline__ double average(double a, double b) {
     double s = sign1(a);
     double c = 0.25 * a + 0.75 * b;
     double d = 0.75 * a + 0.25 * b;
-    double m = fmin(fmin(2. * fabs(a), 2. * s * b), fmin(s * c, s * d));
-    return s * fmax(0., m);
+    double m = gx_min(gx_min(2. * fabs(a), 2. * s * b), gx_min(s * c, s * d));
+    return s * gx_max(0., m);
   }
   if (LIM == GX_LIMITER_WOODWARD) {
     double s = sign1(a);
     double c = 0.5 * (a + b);
-    double m = fmin(fmin(2. * fabs(a), 2. * s * b), s * c);
-    return s * fmax(0., m);
+    double m = gx_min(gx_min(2. * fabs(a), 2. * s * b), s * c);
+    return s * gx_max(0., m);
   }
   if (LIM == GX_LIMITER_SUPERBEE) {
     double s = sign1(b);
-    double av1 = fmin(2. * fabs(b), s * a);
-    double av2 = fmin(fabs(b), 2. * s * a);
-    return s * fmax(0., fmax(av1, av2));
+    double av1 = gx_min(2. * fabs(b), s * a);
+    double av2 = gx_min(fabs(b), 2. * s * a);
+    return s * gx_max(0., gx_max(av1, av2));
   }
   return 0.;
 }
@@ -248,8 +280,8 @@ __device__ __forceinline__ int riemann_hll(const Phys& P, const double (&wl)[8],
   double csl, csr;
   if (FAST) { csl = cfastX(P, wl); csr = cfastX(P, wr); }
   else { csl = csound(P, wl[4], wl[0]); csr = csound(P, wr[4], wr[0]); }
-  double sr = fmax(wl[1] + csl, wr[1] + csr);
-  double sl = fmin(wl[1] - csl, wr[1] - csr);
+  double sr = gx_max(wl[1] + csl, wr[1] + csr);
+  double sl = gx_min(wl[1] - csl, wr[1] - csr);
   I.ul = wl[1]; I.ur = wr[1]; I.sl = sl; I.sr = sr;
   if (sl > 0) { prim2f<MHD>(P, wl, ff); I.mode = PAS_UPL; return 0; }
   if (sr < 0) { prim2f<MHD>(P, wr, ff); I.mode = PAS_UPR; return 0; }
@@ -268,8 +300,8 @@ __device__ __forceinline__ int riemann_hll(const Phys& P, const double (&wl)[8],
 __device__ __forceinline__ int riemann_hllc(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
   double csl = csound(P, wl[4], wl[0]);
   double csr = csound(P, wr[4], wr[0]);
-  double sr = fmax(wl[1] + csl, wr[1] + csr);
-  double sl = fmin(wl[1] - csl, wr[1] - csr);
+  double sr = gx_max(wl[1] + csl, wr[1] + csr);
+  double sl = gx_min(wl[1] - csl, wr[1] - csr);
   I.ul = wl[1]; I.ur = wr[1]; I.sl = sl; I.sr = sr;
   if (sl > 0) { prim2f<false>(P, wl, ff); I.mode = PAS_UPL; return 0; }
   if (sr < 0) { prim2f<false>(P, wr, ff); I.mode = PAS_UPR; return 0; }
@@ -335,11 +367,11 @@ __device__ __forceinline__ double hlld_energy(const Phys& P, const double (&q)[8
   return 0.5 * q[0] * (q[1] * q[1] + q[2] * q[2] + q[3] * q[3]) + P.cv * q[4] + 0.5 * (bx * bx + q[6] * q[6] + q[7] * q[7]);
 }
 
-__device__ __forceinline__ int riemann_hlld(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
+__device__ __forceinline__ int riemann_hlld_ref(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
   double csl = cfastX(P, wl);
   double csr = cfastX(P, wr);
-  double sr = fmax(wl[1] + csl, wr[1] + csr);
-  double sl = fmin(wl[1] - csl, wr[1] - csr);
+  double sr = gx_max(wl[1] + csl, wr[1] + csr);
+  double sl = gx_min(wl[1] - csl, wr[1] - csr);
   I.ul = wl[1]; I.ur = wr[1]; I.sl = sl; I.sr = sr;
   if (sl > 0) { prim2f<true>(P, wl, ff); I.mode = PAS_UPL; return 0; }
   if (sr < 0) { prim2f<true>(P, wr, ff); I.mode = PAS_UPR; return 0; }
@@ -417,6 +449,102 @@ __device__ __forceinline__ int riemann_hlld(const Phys& P, const double (&wl)[8]
   ff[7] = bzs * sM - bx * ws;
   return 0;
 }
+
+#if defined(GX_FLAVOUR_FAST)
+// x * sign(1, s) without touching the FP64 pipe: flip the sign bit of x by the sign bit of s
+__device__ __forceinline__ double mul_sign(double x, double s) {
+  return __hiloint2double(__double2hiint(x) ^ (__double2hiint(s) & 0x80000000), __double2loint(x));
+}
+// Straight-line (select-based) HLLD for the production build: the same expressions as
+// riemann_hlld_ref / src/hlld.f90:48-319, but both star states and the double-star blend are
+// always formed and the region (UL*, UL**, UR**, UR*) is chosen by selects.  One basic block
+// lets ptxas interleave the independent L/R chains (the kernel is FP64-latency bound, not
+// FP64-throughput bound); the two supersonic cases are a rare override at the end.
+__device__ __forceinline__ int riemann_hlld(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
+  const double csl = cfastX(P, wl), csr = cfastX(P, wr);
+  const double sr = gx_max(wl[1] + csl, wr[1] + csr);
+  const double sl = gx_min(wl[1] - csl, wr[1] - csr);
+  I.ul = wl[1]; I.ur = wr[1]; I.sl = sl; I.sr = sr;
+
+  const double bx = 0.5 * (wl[5] + wr[5]);
+  const double bx2 = bx * bx;
+  const double pTL = wl[4] + 0.5 * (bx2 + wl[6] * wl[6] + wl[7] * wl[7]);
+  const double pTR = wr[4] + 0.5 * (bx2 + wr[6] * wr[6] + wr[7] * wr[7]);
+  const double slmul = sl - wl[1], srmur = sr - wr[1];
+  const double mL = wl[0] * slmul, mR = wr[0] * srmur;            // rho_K (S_K - u_K)
+  const double iden = fast_rcp(mR - mL);
+  const double sM = (mR * wr[1] - mL * wl[1] - pTR + pTL) * iden;
+  const double slmsM = sl - sM, srmsM = sr - sM;
+  const double islm = fast_rcp(slmsM), isrm = fast_rcp(srmsM);
+  const double rhostl = mL * islm, rhostr = mR * isrm;
+  double sql, rsql, sqr, rsqr;
+  fast_sqrt_rsqrt(rhostl, sql, rsql);
+  fast_sqrt_rsqrt(rhostr, sqr, rsqr);
+  const double abx = fabs(bx);
+  const double sstl = sM - abx * rsql, sstr = sM + abx * rsqr;
+  const double pst = (mR * pTL - mL * pTR + mL * mR * (wr[1] - wl[1])) * iden;
+
+  // star states of both sides (hlld.f90:116-135, 164-183), degenerate guard by select
+  const double dL = mL * slmsM - bx2, dR = mR * srmsM - bx2;
+  const double rL_ = fast_rcp(dL), rR_ = fast_rcp(dR);
+  // hlld.f90:119-126: den == 0 -> v* = v, w* = w, By* = Bz* = 0, which is what 1/den := 0 produces below
+  const double idL = (dL != 0.0) ? rL_ : 0.0, idR = (dR != 0.0) ? rR_ : 0.0;
+  const double sMuL = sM - wl[1], sMuR = sM - wr[1];
+  const double cL = bx * sMuL * idL, cR = bx * sMuR * idR;         // Bx (S_M - u_K) / den_K
+  const double nL = (wl[0] * (slmul * slmul) - bx2) * idL, nR = (wr[0] * (srmur * srmur) - bx2) * idR;
+  const double vL = wl[2] - wl[6] * cL, wLs = wl[3] - wl[7] * cL;
+  const double vR = wr[2] - wr[6] * cR, wRs = wr[3] - wr[7] * cR;
+  const double byL = wl[6] * nL, bzL = wl[7] * nL;
+  const double byR = wr[6] * nR, bzR = wr[7] * nR;
+
+  // double-star state (hlld.f90:207-253)
+  const double idd = fast_rcp(sql + sqr), sq2 = sql * sqr;
+  const double vss = (sql * vL + sqr * vR + mul_sign(byR - byL, bx)) * idd;
+  const double wss = (sql * wLs + sqr * wRs + mul_sign(bzR - bzL, bx)) * idd;
+  const double byss = (sql * byR + sqr * byL + sq2 * mul_sign(vR - vL, bx)) * idd;
+  const double bzss = (sql * bzR + sqr * bzL + sq2 * mul_sign(wRs - wLs, bx)) * idd;
+  const double vdb_ss = sM * bx + vss * byss + wss * bzss;
+
+  // region: hlld.f90 tests sstl>=0, sstr<=0, sM>=0, sM<=0 in this order
+  const bool starL = sstl >= 0.0, starR = !starL && (sstr <= 0.0);
+  const bool dstar = !(starL || starR);
+  const bool left = starL || (dstar && sM >= 0.0);
+  const int err = (dstar && !(sM >= 0.0) && !(sM <= 0.0)) ? 1 : 0;     // NaN: 'Error in HLLD routine' + stop
+
+  // outer state K = L | R by select, then one energy evaluation (hlld.f90:113-114, 137-156)
+  const double q0 = left ? wl[0] : wr[0], q1 = left ? wl[1] : wr[1], q2 = left ? wl[2] : wr[2], q3 = left ? wl[3] : wr[3];
+  const double q4 = left ? wl[4] : wr[4], q6 = left ? wl[6] : wr[6], q7 = left ? wl[7] : wr[7];
+  const double sKmu = left ? slmul : srmur, iK = left ? islm : isrm, pTK = left ? pTL : pTR;
+  const double rhost = left ? rhostl : rhostr;
+  const double vK = left ? vL : vR, wK = left ? wLs : wRs, byK = left ? byL : byR, bzK = left ? bzL : bzR;
+  const double sqK = left ? -sql : sqr;
+  const double eK = 0.5 * q0 * (q1 * q1 + q2 * q2 + q3 * q3) + P.cv * q4 + 0.5 * (bx2 + q6 * q6 + q7 * q7);
+  const double vdotb = q1 * bx + q2 * q6 + q3 * q7;
+  const double vsdotbs = sM * bx + vK * byK + wK * bzK;
+  const double estK = (sKmu * eK - pTK * q1 + pst * sM + bx * (vdotb - vsdotbs)) * iK;
+  const double es = dstar ? estK + sqK * mul_sign(vsdotbs - vdb_ss, bx) : estK;
+  const double vs = dstar ? vss : vK, ws = dstar ? wss : wK, bys = dstar ? byss : byK, bzs = dstar ? bzss : bzK;
+  const double vdb = dstar ? vdb_ss : vsdotbs;
+  I.mode = left ? PAS_HLLD_L : PAS_HLLD_R; I.a = sM; I.b = sKmu; I.c = left ? slmsM : srmsM;
+
+  const double rsm = rhost * sM;
+  ff[0] = rsm;
+  ff[1] = rsm * sM + pst - bx2;
+  ff[2] = rsm * vs - bx * bys;
+  ff[3] = rsm * ws - bx * bzs;
+  ff[4] = sM * (es + pst) - bx * vdb;
+  ff[5] = 0.;
+  ff[6] = bys * sM - bx * vs;
+  ff[7] = bzs * sM - bx * ws;
+  if (sl > 0.0) { prim2f<true>(P, wl, ff); I.mode = PAS_UPL; return 0; }     // supersonic: rare
+  if (sr < 0.0) { prim2f<true>(P, wr, ff); I.mode = PAS_UPR; return 0; }
+  return err;
+}
+#else
+__device__ __forceinline__ int riemann_hlld(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
+  return riemann_hlld_ref(P, wl, wr, ff, I);
+}
+#endif
 
 template <int SOLVER>
 __device__ __forceinline__ int riemann(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {

@@ -34,6 +34,9 @@
 #ifndef GX_STAGE_SOLVER
 #error "define GX_STAGE_SOLVER (1..4)"
 #endif
+#ifndef GX_STAGE1_MINBLOCKS
+#define GX_STAGE1_MINBLOCKS 1
+#endif
 
 namespace gx {
 namespace GX_NS {
@@ -50,6 +53,24 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// Split CTA barriers on mbarriers (arrive early, wait late): with one CTA per SM a full
+// __syncthreads idles the SM, so every hand-over in the plane loop is an arrive followed,
+// as late as the data dependence allows, by a parity wait.  All NT threads arrive once per
+// plane on each barrier; phase parity = plane counter & 1.
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "MBAR_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n\t"
+      "@!p bra MBAR_WAIT_%=;\n\t}"
+      ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
 
 template <int NQ_, int ORDER_>
 struct StageGeom {
@@ -99,7 +120,8 @@ struct FaceJob {
 };
 
 template <int SOLVER, int LIM, int ORDER, int NQ, int PC>
-__device__ __forceinline__ int solve_job(const gxp::Phys& P, const double* ring, double* xch, const FaceJob& J) {
+__device__ __forceinline__ int solve_job(const gxp::Phys& P, const double* ring, double* xch, const FaceJob& J,
+                                         unsigned long long* bar_free, int free_parity) {
   double wl[8], wr[8], fr[8];
   {
     const int off[8] = {0, J.vn, J.vt1, J.vt2, 4 * PC, J.vn + 4 * PC, J.vt1 + 4 * PC, J.vt2 + 4 * PC};
@@ -112,6 +134,7 @@ __device__ __forceinline__ int solve_job(const gxp::Phys& P, const double* ring,
   }
   gxp::PasInfo I;
   const int err = gxp::riemann<SOLVER>(P, wl, wr, fr, I);
+  if (free_parity >= 0) mbar_wait(bar_free, free_parity);   // every warp has finished reading the previous plane's fluxes
   if (J.store) {
     double* o = xch + J.out;
     const int oc[8] = {0, J.on, J.ot1, J.ot2, 4, J.on + 4, J.ot1 + 4, J.ot2 + 4};
@@ -122,7 +145,7 @@ __device__ __forceinline__ int solve_job(const gxp::Phys& P, const double* ring,
 }
 
 template <int SOLVER, int LIM, int ORDER, bool FLUXCD>
-__global__ void __launch_bounds__(StageGeom<(SOLVER == GX_SOLVER_HLLE || SOLVER == GX_SOLVER_HLLD) ? 8 : 5, ORDER>::NT, 1)
+__global__ void __launch_bounds__(StageGeom<(SOLVER == GX_SOLVER_HLLE || SOLVER == GX_SOLVER_HLLD) ? 8 : 5, ORDER>::NT, (ORDER == 1 ? GX_STAGE1_MINBLOCKS : 1))
 k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const double* Ub, double* dst,
         double* __restrict__ E, const int kz, unsigned long long* dtmin_bits, const int want_cfl, int* errflag) {
   constexpr bool MHD = (SOLVER == GX_SOLVER_HLLE || SOLVER == GX_SOLVER_HLLD);
@@ -146,109 +169,128 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
   const long long vs = g.vs;
 
   // ---- plane staging: conserved -> shared (cp.async), converted in place to primitives ----
+  // Ownership: a main-warp thread stages and converts ITS OWN centre cell (so its z solves, which
+  // only read its own column, never wait for another thread), and the halo frame of the plane
+  // (consumed ORDER+1 planes later by the x/y solves) is dealt round-robin.
+  const bool main_warp = wrp < TY;
+  const int cidx = (min(wrp, TY - 1) + H) * CX + (lane + H);   // this thread's cell inside a staged plane
+  constexpr int HC = PC - TY * TX;                       // halo cells of a staged plane
+  auto halo_cell = [&](int h) {                          // h-th halo cell -> plane-local index
+    if (h < H * CX) return h;                                                   // rows below the tile
+    if (h < H * CX + 2 * H * TY) {
+      const int t = h - H * CX, r = t / (2 * H), sx = t - r * (2 * H);
+      return (H + r) * CX + (sx < H ? sx : TX + sx);                            // left | right columns
+    }
+    return h - (H * CX + 2 * H * TY) + (H + TY) * CX;                           // rows above the tile
+  };
   auto slot_off = [&](int p) { return ((p - (k0 - H)) % NSLOT) * G::PLANE; };
+  auto stage_cell = [&](double* sl, int c, int kk) {
+    const int rr = c / CX, cc = c - rr * CX;
+    int i = min(i0 - H + cc, g.nx + 2), j = min(j0 - H + rr, g.ny + 2);
+    if (A.wrap[0]) i = i < 1 ? i + g.nx : (i > g.nx ? i - g.nx : i);
+    if (A.wrap[1]) j = j < 1 ? j + g.ny : (j > g.ny ? j - g.ny : j);
+    const double* src = S + g.idx(i, j, kk);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) cp_async8(sl + q * PC + c, src + q * vs);
+  };
   auto issue_load = [&](int p) {
     double* sl = ring + slot_off(p);
-    const int kk = min(p, g.nz + 2);
-    for (int c = tid; c < PC; c += NT) {
-      const int rr = c / CX, cc = c - rr * CX;
-      const int i = min(i0 - H + cc, g.nx + 2), j = min(j0 - H + rr, g.ny + 2);
-      const double* src = S + g.idx(i, j, kk);
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) cp_async8(sl + q * PC + c, src + q * vs);
-    }
+    int kk = min(p, g.nz + 2);
+    if (A.wrap[2]) kk = kk < 1 ? kk + g.nz : (kk > g.nz ? kk - g.nz : kk);
+    if (main_warp) stage_cell(sl, cidx, kk);
+    for (int h = tid; h < HC; h += NT) stage_cell(sl, halo_cell(h), kk);
     cp_async_commit();
+  };
+  auto convert_cell = [&](double* sl, int c) {
+    double u[8], w[8], T;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) u[q] = sl[q * PC + c];
+    gxp::u2prim<MHD, false>(A.phys, u, w, 0.0, T);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) sl[q * PC + c] = w[q];
   };
   auto convert = [&](int p) {      // each thread converts exactly the cells it staged itself
     double* sl = ring + slot_off(p);
-    for (int c = tid; c < PC; c += NT) {
-      double u[8], w[8], T;
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) u[q] = sl[q * PC + c];
-      gxp::u2prim<MHD>(A.phys, u, w, 0.0, T);
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) sl[q * PC + c] = w[q];
-    }
+    if (main_warp) convert_cell(sl, cidx);
+    for (int h = tid; h < HC; h += NT) convert_cell(sl, halo_cell(h));
   };
 
+  // Barriers of the plane loop (all NT threads arrive once per plane on each):
+  //   bars[0] XY   : x and y face fluxes of this plane are in the exchange buffers
+  //   bars[1] FREE : this thread has consumed the exchange buffers (they may be overwritten)
+  // The z flux is handed over in thread-private slots and the newest plane's centre cell is
+  // converted by its consumer, so neither needs a CTA-wide barrier.
+  __shared__ unsigned long long bars[2];
+  if (tid == 0) { mbar_init(&bars[0], NT); mbar_init(&bars[1], NT); }
+#pragma unroll 1
   for (int p = k0 - H; p <= k0 + H - 1; ++p) issue_load(p);
   cp_async_wait_all();
+#pragma unroll 1
   for (int p = k0 - H; p <= k0 + H - 1; ++p) convert(p);
   __syncthreads();
 
-  const bool main_warp = wrp < TY;
   const int i = i0 + lane, j = j0 + wrp;
   const bool cell_ok = main_warp && i <= g.nx && j <= g.ny;
   const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
-  const int cidx = (wrp + H) * CX + (lane + H);          // this thread's cell inside a staged plane
   double hprev[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) hprev[q] = 0.0;
   double dtp = 1.e30;
   int err = 0;
+  int it = 0;                                             // plane counter (barrier phase)
 
-  for (int k = k0 - 1; k <= kend; ++k) {
-    if (k < kend) issue_load(k + H + 1);                  // lands in the slot of plane k-H (free since the last barrier)
+  for (int k = k0 - 1; k <= kend; ++k, ++it) {
+    if (k < kend) issue_load(k + H + 1);                  // into the slot of plane k-H: its last readers were this thread's
+                                                          // own z solve (centre) and x/y solves >= 1 XY barrier ago (halo)
     const int sk = slot_off(k);
-    // jobs of this thread: main warps solve the lower x face, the lower y face and the upper z face
+    const bool xy = k >= k0;
+    // jobs of this thread: main warps solve the lower y face, the lower x face and the upper z face
     // of their cell; warp TY closes the tile (y faces above the last row, x faces right of the last column)
     const int njobs = main_warp ? 3 : 2;
     double ub[8];
     const long long cg = g.idx(min(i, g.nx), min(j, g.ny), max(k, 1));
 #pragma unroll 1
-    for (int jb = (k >= k0 ? 0 : 2); jb < njobs; ++jb) {
+    for (int jb = (xy ? 0 : 2); jb < njobs; ++jb) {
       FaceJob J;
-      if (main_warp) {
-        if (jb == 0) {                                    // lower x face of (i,j,k)
-          const int c = sk + cidx;
-          J.o_m2 = c - 2; J.o_m1 = c - 1; J.o_p0 = c; J.o_p1 = c + 1;
-          J.on = 1; J.ot1 = 2; J.ot2 = 3;
-          J.out = XB0 + wrp * (TX + 1) + lane; J.ovs = XBV;
-          J.store = true; J.check = (i <= g.nx + 1 && j <= g.ny);
-        } else if (jb == 1) {                             // lower y face
-          const int c = sk + cidx;
-          J.o_m2 = c - 2 * CX; J.o_m1 = c - CX; J.o_p0 = c; J.o_p1 = c + CX;
-          J.on = 2; J.ot1 = 1; J.ot2 = 3;
-          J.out = YB0 + wrp * TX + lane; J.ovs = YBV;
-          J.store = true; J.check = (i <= g.nx && j <= g.ny + 1);
-        } else {                                          // upper z face: planes k-H+1 .. k+H
-          J.o_m1 = sk + cidx; J.o_p0 = slot_off(k + 1) + cidx;
-          J.o_m2 = (ORDER == 2) ? slot_off(k - 1) + cidx : J.o_m1;
-          J.o_p1 = (ORDER == 2) ? slot_off(k + 2) + cidx : J.o_p0;
-          J.on = 3; J.ot1 = 2; J.ot2 = 1;
-          J.out = ZB0 + wrp * TX + lane; J.ovs = ZBV;
-          J.store = true; J.check = cell_ok;
-          if (k >= k0) {                                  // base state for the update: in flight during the z solve
+      if (jb == 0) {                                      // lower y face (extra warp: the row above the tile)
+        const int c = sk + cidx + (main_warp ? 0 : CX);
+        J.o_m2 = c - 2 * CX; J.o_m1 = c - CX; J.o_p0 = c; J.o_p1 = c + CX;
+        J.on = 2; J.ot1 = 1; J.ot2 = 3;
+        J.out = YB0 + wrp * TX + lane; J.ovs = YBV;
+        J.store = true; J.check = (i <= g.nx && j <= g.ny + 1);
+      } else if (jb == 1) {                               // lower x face (extra warp: right of the last column, row = lane)
+        const int row = main_warp ? wrp : min(lane, TY - 1), col = main_warp ? lane : TX;
+        const int c = sk + (row + H) * CX + (col + H);
+        J.o_m2 = c - 2; J.o_m1 = c - 1; J.o_p0 = c; J.o_p1 = c + 1;
+        J.on = 1; J.ot1 = 2; J.ot2 = 3;
+        J.out = XB0 + row * (TX + 1) + col; J.ovs = XBV;
+        J.store = main_warp || lane < TY;
+        J.check = main_warp ? (i <= g.nx + 1 && j <= g.ny) : (lane < TY && i0 + TX <= g.nx + 1 && j0 + lane <= g.ny);
+      } else {                                            // upper z face: planes k-H+1 .. k+H, own column only
+        J.o_m1 = sk + cidx; J.o_p0 = slot_off(k + 1) + cidx;
+        J.o_m2 = (ORDER == 2) ? slot_off(k - 1) + cidx : J.o_m1;
+        J.o_p1 = (ORDER == 2) ? slot_off(k + 2) + cidx : J.o_p0;
+        J.on = 3; J.ot1 = 2; J.ot2 = 1;
+        J.out = ZB0 + wrp * TX + lane; J.ovs = ZBV;
+        J.store = true; J.check = cell_ok;
+        if (xy) {                                         // base state for the update: in flight during the z solve
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) if (!(FLUXCD && q >= 5)) ub[q] = Ub[q * vs + cg];
-          }
-        }
-      } else {
-        if (jb == 0) {                                    // y faces above the last row of the tile
-          const int c = sk + (TY + H) * CX + (lane + H);
-          J.o_m2 = c - 2 * CX; J.o_m1 = c - CX; J.o_p0 = c; J.o_p1 = c + CX;
-          J.on = 2; J.ot1 = 1; J.ot2 = 3;
-          J.out = YB0 + TY * TX + lane; J.ovs = YBV;
-          J.store = true; J.check = (i <= g.nx && j0 + TY <= g.ny + 1);
-        } else {                                          // x faces right of the last column: row = lane
-          const int row = min(lane, TY - 1);
-          const int c = sk + (row + H) * CX + (TX + H);
-          J.o_m2 = c - 2; J.o_m1 = c - 1; J.o_p0 = c; J.o_p1 = c + 1;
-          J.on = 1; J.ot1 = 2; J.ot2 = 3;
-          J.out = XB0 + row * (TX + 1) + TX; J.ovs = XBV;
-          J.store = lane < TY; J.check = (lane < TY && i0 + TX <= g.nx + 1 && j0 + lane <= g.ny);
+          for (int q = 0; q < NQ; ++q) if (!(FLUXCD && q >= 5)) ub[q] = Ub[q * vs + cg];
         }
       }
       J.vn = J.on * PC; J.vt1 = J.ot1 * PC; J.vt2 = J.ot2 * PC;
-      err |= solve_job<SOLVER, LIM, ORDER, NQ, PC>(A.phys, ring, xch, J);
+      // the first x/y store of a plane waits until every thread has consumed the previous plane's fluxes
+      err |= solve_job<SOLVER, LIM, ORDER, NQ, PC>(A.phys, ring, xch, J, &bars[1], (jb == 0 && it > 0) ? ((it - 1) & 1) : -1);
+      if (jb == 1) mbar_arrive(&bars[0]);                 // my x and y fluxes are written
     }
-    __syncthreads();                                      // face fluxes visible
+    if (!xy) mbar_arrive(&bars[0]);                       // (no x/y faces on the chunk's leading plane)
     double h[8];
     if (main_warp) {
 #pragma unroll
       for (int q = 0; q < NQ; ++q) h[q] = zb[q * ZBV + wrp * TX + lane];
     }
-    if (k >= k0 && cell_ok) {
+    mbar_wait(&bars[0], it & 1);                          // all x/y face fluxes of this plane visible
+    if (xy && cell_ok) {
       const long long c = g.idx(i, j, k);
       double un[8];
 #pragma unroll
@@ -271,7 +313,7 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
         E[2 * vs + c] = 0.25 * (-f6l - f6u + g5l + g5u);
       } else if (want_cfl) {                              // get_timestep candidates of the new state, hydro_core.f90:644-675
         double w[8], T;
-        gxp::u2prim<MHD>(A.phys, un, w, 0.0, T);
+        gxp::u2prim<MHD, false>(A.phys, un, w, 0.0, T);
         if (MHD) {
           double cx, cy, cz;
           gxp::cfast3(A.phys, w[4], w[0], w[5], w[6], w[7], cx, cy, cz);
@@ -286,11 +328,12 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
         }
       }
     }
+    mbar_arrive(&bars[1]);                                // done reading the exchange buffers
 #pragma unroll
     for (int q = 0; q < NQ; ++q) hprev[q] = h[q];
-    if (k < kend) { cp_async_wait_all(); convert(k + H + 1); }
-    __syncthreads();                                      // next plane ready; exchange buffers free
+    if (k < kend) { cp_async_wait_all(); convert(k + H + 1); }   // next plane -> primitives (own cells)
   }
+  __syncthreads();
   if (err) atomicOr(errflag, 1);
   if (!FLUXCD && want_cfl) stage_block_min<NT>(dtp, dtmin_bits, xch);
 }
