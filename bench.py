@@ -48,7 +48,8 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region."""
+    """nvidia-smi clocks + throttle reasons DURING the timed region (sampled from before the
+    warm-up; only the samples whose host timestamp falls inside the timed window are kept)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -59,7 +60,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.idx)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.idx)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -68,18 +69,24 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0: float, t1: float):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        inside = [ln for (t, ln) in self.lines if t0 <= t <= t1 + 0.03]
+        note = None
+        if not inside:       # window shorter than the sampling period: nearest samples after the start
+            inside = [ln for (t, ln) in self.lines if t >= t0][:2] or [ln for (_t, ln) in self.lines[-2:]]
+            note = "timed window shorter than the sampling period; nearest samples used"
         sm, smax, reasons, power = [], [], set(), []
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -92,8 +99,11 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+               "samples": len(sm), "reasons": sorted(reasons)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def workload(n_per_gpu: int, world: int) -> Params:
@@ -143,7 +153,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=256, help="cells per side of the per-GPU block")
@@ -189,19 +199,21 @@ def main():
         return float(t.item())
 
     # ---------------- device-resident throughput ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     blk.set_state(u0)
     tsim, it = 0.0, 1
     tsim, it, _ = blk.run(args.warmup, tsim, it)
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
     l0 = blk.launch_count
+    tw0 = time.time()
     tsim, it, last_dt = blk.run(args.steps, tsim, it)
+    tw1 = time.time()
     ms = blk.last_elapsed_ms
     l1 = blk.launch_count
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     ms = max_over_ranks(ms)
     value = zones_total * args.steps / (ms * 1e-3)
 
@@ -234,6 +246,18 @@ def main():
     e2e_value = zones_total * e2e_steps / e2e_sec if e2e_steps > 0 else None
     state_bytes = int(uh.nbytes)
     finite = bool(np.isfinite(uh).all())
+    # the loop a Fortran host runs between outputs (main.f90:94-125): state stays resident, only
+    # dt / dump_flag cross the C ABI every step (wall clock, host-driven, one sync per step)
+    res_steps = max(3, min(args.steps, 20))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(res_steps):
+        dt, _d = blk.get_timestep(it_e, 10, t_e, 1e300)
+        blk.tstep(dt)
+        t_e += dt; it_e += 1
+    torch.cuda.synchronize()
+    res_sec = max_over_ranks(time.perf_counter() - t0)
+    barrier()
 
     if rank != 0:
         if world > 1:
@@ -242,16 +266,36 @@ def main():
 
     peak_gbs, peak_src = measured_peaks()
     step_ms = ms / args.steps
-    achieved_gbs = BYTES_PER_ZONE * zones_rank / (step_ms * 1e-3) / 1e9
-    flux_ms, flux_n = ktimes["flux"]
     tot_prof = sum(v[0] for v in ktimes.values())
+    fused = ktimes["stage2"][1] > 0
+    if fused:
+        # dominant kernel: the fused 2nd-order stage (k_stage<HLLD,minmod,2,fluxcd>); its algorithmic
+        # traffic is: read U* (neq) and U^n (neq), write U^{n+1} (neq) = 3*neq doubles per zone
+        dom_name, dom_key, dom_bytes_zone = "k_stage<HLLD,minmod,ORDER=2,fluxCD> (fused prim+3 sweeps+E+update)", "stage2", 3 * 8 * pb.neq
+    else:
+        dom_name, dom_key, dom_bytes_zone = "k_flux<HLLD,minmod> (3 launches per stage, unfused path)", "flux", 2 * 8 * pb.neq * 3
+    dom_ms, dom_n = ktimes[dom_key]
+    dom_avg_ms = dom_ms / dom_n if dom_n else None
+    dom_gbs = dom_bytes_zone * zones_rank / (dom_avg_ms * 1e-3) / 1e9 if dom_avg_ms else None
+    traffic = None
+    try:       # DRAM bytes of that kernel per launch from the committed ncu --set full capture (same workload only)
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tj = json.load(f)
+        if fused and tj.get("zones") == zones_rank:
+            traffic = tj["stage2_dram_bytes_per_launch"]
+    except Exception:
+        pass
+    step_gbs = BYTES_PER_ZONE * zones_rank / (step_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "achieved": achieved_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": achieved_gbs / peak_gbs, "traffic": None,
-        "peak_source": peak_src,
-        "definition": "320 B algorithmic per zone-update x zones per GPU / whole-step device time (all kernels of one tstep)",
-        "kernel_share": {k: (v[0] / tot_prof if tot_prof > 0 else None) for k, v in ktimes.items()},
-        "kernel_ms_per_step": {k: v[0] / nprof for k, v in ktimes.items()},
-        "dominant_kernel": "flux sweeps (k_flux<HLLD,minmod>)", "dominant_avg_launch_ms": (flux_ms / flux_n if flux_n else None),
+        "bound": "hbm", "achieved": dom_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": (dom_gbs / peak_gbs if dom_gbs else None), "traffic": traffic,
+        "peak_source": peak_src, "kernel": dom_name, "avg_launch_ms": dom_avg_ms,
+        "algorithmic_bytes_per_zone": dom_bytes_zone,
+        "definition": "algorithmic bytes of the dominant kernel (3*neq doubles per zone) x zones per GPU / its average launch time (CUDA events on the solver's stream)",
+        "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak_gbs, "algorithmic_bytes_per_zone": BYTES_PER_ZONE,
+                       "definition": "320 B per zone-update (5*neq doubles) x zones per GPU / whole-step device time"},
+        "fp64_note": "the kernel is FP64-pipe/latency bound, not HBM bound: see profiles/ (sm__inst_executed_pipe_fp64 ~43%, dram ~15%) and DESIGN.md",
+        "kernel_share": {k: (v[0] / tot_prof if tot_prof > 0 else None) for k, v in ktimes.items() if v[1]},
+        "kernel_ms_per_step": {k: v[0] / nprof for k, v in ktimes.items() if v[1]},
     }
     cpu = None
     if not args.no_cpu_baseline:
@@ -265,12 +309,14 @@ def main():
         "config": {"workload": f"3-D Orszag-Tang {args.n}^3 per GPU (BASELINE configs[1]), HLLD + flux-CD, minmod, periodic, cfl 0.2",
                    "grid_total": [pb.nxtot, pb.nytot, pb.nztot], "blocks": list(nb), "neq": pb.neq,
                    "kernels": "strict (-fmad=false)" if args.strict else "fast (-fmad=true)",
-                   "l2": "working set (u,up,W,F,E > 3 GB per GPU) exceeds the 126 MB L2; no flush needed",
+                   "l2": "working set (u, up, E: 2.7 GB per GPU at 256^3) exceeds the 126 MB L2; no flush needed",
                    "halo_bytes_per_step_per_gpu": halo_bytes_per_step(pb)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes + 16,
                 "steps": e2e_steps, "ms_per_step": (e2e_sec / e2e_steps * 1e3 if e2e_steps > 0 else None),
                 "path": "gx_set_state(host u) -> gx_get_timestep -> gx_tstep -> gx_get_state(host u) through libguacho_gx.so"},
+        "e2e_resident": {"value": zones_total * res_steps / res_sec, "unit": UNIT, "steps": res_steps, "ms_per_step": res_sec / res_steps * 1e3,
+                         "path": "gx_get_timestep -> gx_tstep per step, state resident on the device (the reference host's loop between outputs)"},
         "gpu_launches": int(l1 - l0),
         "roofline": roofline,
         "cpu_baseline": cpu,

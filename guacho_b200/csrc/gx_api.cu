@@ -283,9 +283,13 @@ static int exchange_dir(gx_solver* s, double* A, int nvar, int nl, int dir) {
   double *recv_lo = s->halo_recv[2 * dir], *recv_hi = s->halo_recv[2 * dir + 1];
   if (lo >= 0) launch_pack(s, nvar, A, send_lo, sb_lo, 0);
   if (hi >= 0) launch_pack(s, nvar, A, send_hi, sb_hi, 0);
+  // Message order matters when lo == hi (two blocks, periodic): NCCL pairs the sends and receives of
+  // one peer in issue order, and my upward message must land in the peer's LOW ghost layers.
   NCCL_TRY(g_nccl.GroupStart());
-  if (hi >= 0) { NCCL_TRY(g_nccl.Send(send_hi, cnt, ncclDouble, hi, s->comm, s->stream)); NCCL_TRY(g_nccl.Recv(recv_hi, cnt, ncclDouble, hi, s->comm, s->stream)); }
-  if (lo >= 0) { NCCL_TRY(g_nccl.Send(send_lo, cnt, ncclDouble, lo, s->comm, s->stream)); NCCL_TRY(g_nccl.Recv(recv_lo, cnt, ncclDouble, lo, s->comm, s->stream)); }
+  if (hi >= 0) NCCL_TRY(g_nccl.Send(send_hi, cnt, ncclDouble, hi, s->comm, s->stream));
+  if (lo >= 0) NCCL_TRY(g_nccl.Recv(recv_lo, cnt, ncclDouble, lo, s->comm, s->stream));
+  if (lo >= 0) NCCL_TRY(g_nccl.Send(send_lo, cnt, ncclDouble, lo, s->comm, s->stream));
+  if (hi >= 0) NCCL_TRY(g_nccl.Recv(recv_hi, cnt, ncclDouble, hi, s->comm, s->stream));
   NCCL_TRY(g_nccl.GroupEnd());
   if (lo >= 0) launch_pack(s, nvar, A, recv_lo, face_box(g, dir, 0, nl, true), 1);
   if (hi >= 0) launch_pack(s, nvar, A, recv_hi, face_box(g, dir, 1, nl, true), 1);
