@@ -34,6 +34,9 @@
 #ifndef GX_STAGE_SOLVER
 #error "define GX_STAGE_SOLVER (1..4)"
 #endif
+#ifndef GX_STAGE2_MINBLOCKS
+#define GX_STAGE2_MINBLOCKS 1
+#endif
 #ifndef GX_STAGE1_MINBLOCKS
 #define GX_STAGE1_MINBLOCKS 1
 #endif
@@ -145,7 +148,7 @@ __device__ __forceinline__ int solve_job(const gxp::Phys& P, const double* ring,
 }
 
 template <int SOLVER, int LIM, int ORDER, bool FLUXCD>
-__global__ void __launch_bounds__(StageGeom<(SOLVER == GX_SOLVER_HLLE || SOLVER == GX_SOLVER_HLLD) ? 8 : 5, ORDER>::NT, (ORDER == 1 ? GX_STAGE1_MINBLOCKS : 1))
+__global__ void __launch_bounds__(StageGeom<(SOLVER == GX_SOLVER_HLLE || SOLVER == GX_SOLVER_HLLD) ? 8 : 5, ORDER>::NT, (ORDER == 1 ? GX_STAGE1_MINBLOCKS : GX_STAGE2_MINBLOCKS))
 k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const double* Ub, double* dst,
         double* __restrict__ E, const int kz, unsigned long long* dtmin_bits, const int want_cfl, int* errflag) {
   constexpr bool MHD = (SOLVER == GX_SOLVER_HLLE || SOLVER == GX_SOLVER_HLLD);

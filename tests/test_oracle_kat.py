@@ -1,0 +1,256 @@
+"""Known-answer tests of the CPU oracle (KATs 1-7) — no GPU needed.
+
+These are properties that follow from the reference code itself (src/*.f90) and so pin the
+restatement where the reference offers no golden vectors: solver consistency and upwinding,
+limiter values, fixed points, axis-permutation equivalence, conservation, div B under flux-CD,
+the Orszag-Tang symmetry, and invariance under the MPI block decomposition.
+"""
+import numpy as np
+import pytest
+
+from guacho_b200.config import (Params, SOLVER_HLL, SOLVER_HLLC, SOLVER_HLLE, SOLVER_HLLD, ALL_LIMITERS,
+                                LIMITER_NO_AVERAGE, LIMITER_NO_LIMIT, LIMITER_MINMOD, LIMITER_VAN_LEER,
+                                LIMITER_VAN_ALBADA, LIMITER_UMIST, LIMITER_WOODWARD, LIMITER_SUPERBEE,
+                                BC_OUTFLOW, BC_CLOSED)
+from tests.oracle_lib import Oracle, U, UP, PRIMIT, load
+from tests.util import global_ic, oracle_from_ic
+
+SOLVERS = [(SOLVER_HLL, False), (SOLVER_HLLC, False), (SOLVER_HLLE, True), (SOLVER_HLLD, True)]
+
+
+def _par(solver, mhd, **kw):
+    base = dict(nxtot=8, nytot=8, nztot=8, zmax=1.0, mhd=mhd, riemann_solver=solver, enable_flux_cd=False)
+    base.update(kw)
+    return Params(**base)
+
+
+def _states(neq, n, seed):
+    rng = np.random.default_rng(seed)
+    W = np.zeros((n, neq))
+    W[:, 0] = rng.uniform(0.3, 2.0, n)
+    W[:, 1:4] = rng.normal(0, 0.6, (n, 3))
+    W[:, 4] = rng.uniform(0.2, 2.0, n)
+    if neq >= 8:
+        W[:, 5:8] = rng.normal(0, 0.5, (n, 3))
+    return W
+
+
+# ---- KAT 1: consistency and upwinding ---------------------------------------------------
+@pytest.mark.parametrize("solver,mhd", SOLVERS)
+def test_consistency_F_of_equal_states_is_physical_flux(solver, mhd):
+    o = Oracle(_par(solver, mhd))
+    for w in _states(o.p.neq, 64, 1):
+        f, err = o.riemann(w, w)
+        ref = o.prim2f(w)
+        assert err == 0
+        assert np.abs(f - ref).max() <= 2e-14 * (np.abs(ref).max() + 1.0)
+
+
+@pytest.mark.parametrize("solver,mhd", SOLVERS)
+def test_supersonic_states_are_upwinded_exactly(solver, mhd):
+    o = Oracle(_par(solver, mhd))
+    W = _states(o.p.neq, 32, 2)
+    for a, b in zip(W[::2], W[1::2]):
+        l, r = a.copy(), b.copy()
+        l[1] += 8.0; r[1] += 8.0                      # sl > 0  -> prim2f(L)  (hlld.f90:71-74)
+        assert np.array_equal(o.riemann(l, r)[0], o.prim2f(l))
+        l[1] -= 16.0; r[1] -= 16.0                    # sr < 0  -> prim2f(R)  (hlld.f90:77-80)
+        assert np.array_equal(o.riemann(l, r)[0], o.prim2f(r))
+
+
+def test_hlld_normal_field_flux_is_zero_and_mirror_symmetric():
+    """ff(6)=0 always (hlld.f90:147); reflecting x (u -> -u, Bx -> -Bx, L<->R) flips the sign of the
+    mass/energy/transverse fluxes and keeps the normal momentum flux."""
+    o = Oracle(_par(SOLVER_HLLD, True))
+    W = _states(8, 64, 3)
+    for l, r in zip(W[::2], W[1::2]):
+        r[5] = l[5]
+        f, _ = o.riemann(l, r)
+        assert f[5] == 0.0
+        lm, rm = r.copy(), l.copy()
+        for s in (lm, rm):
+            s[1] = -s[1]; s[5] = -s[5]
+        fm, _ = o.riemann(lm, rm)
+        sgn = np.array([-1, 1, -1, -1, -1, 1, -1, -1.0])
+        assert np.abs(fm - sgn * f).max() <= 1e-12 * (np.abs(f).max() + 1)
+
+
+# ---- limiter values (src/hydro_core.f90:741-794) -----------------------------------------
+def test_limiter_averages_known_values():
+    L = load()
+    av = lambda lim, a, b: L.orc_average(lim, a, b)
+    assert av(LIMITER_NO_AVERAGE, 1.0, 3.0) == 0.0
+    assert av(LIMITER_NO_LIMIT, 1.0, 3.0) == 2.0
+    assert av(LIMITER_MINMOD, 1.0, 3.0) == 1.0 and av(LIMITER_MINMOD, -3.0, -1.0) == -1.0
+    assert av(LIMITER_MINMOD, -1.0, 3.0) == 0.0 and av(LIMITER_MINMOD, 1.0, 0.0) == 0.0
+    assert av(LIMITER_VAN_LEER, 1.0, 3.0) == 1.0 * 3.0 * 4.0 / 10.0 and av(LIMITER_VAN_LEER, -1.0, 3.0) == 0.0
+    d = 1e-7
+    assert av(LIMITER_VAN_ALBADA, 1.0, 3.0) == (1.0 * (9.0 + d) + 3.0 * (1.0 + d)) / (1.0 + 9.0 + d)
+    assert av(LIMITER_UMIST, 1.0, 3.0) == min(2.0, 6.0, 0.25 + 2.25, 0.75 + 0.75)
+    assert av(LIMITER_WOODWARD, 1.0, 3.0) == min(2.0, 6.0, 2.0) and av(LIMITER_WOODWARD, 1.0, -3.0) == 0.0
+    assert av(LIMITER_SUPERBEE, 1.0, 3.0) == max(min(6.0, 1.0), min(3.0, 2.0))
+    for lim in ALL_LIMITERS[2:]:                      # all real limiters: zero at an extremum, s at equal slopes
+        assert av(lim, 1.0, -1.0) == 0.0
+        assert abs(av(lim, 0.5, 0.5) - 0.5) < 1e-7
+
+
+def test_limiter_reconstructs_linear_data_exactly_and_flattens_extrema():
+    p = _par(SOLVER_HLLD, True, slope_limiter=LIMITER_MINMOD)
+    o = Oracle(p)
+    base = np.arange(1, 9, dtype=float)
+    pl, pr = o.limiter(base, base + 1.0, base + 2.0, base + 3.0)       # slopes all 1
+    assert np.array_equal(pl, base + 1.5) and np.array_equal(pr, base + 1.5)
+    pl, pr = o.limiter(base + 1.0, base, base + 1.0, base)             # zig-zag: first order
+    assert np.array_equal(pl, base) and np.array_equal(pr, base + 1.0)
+
+
+def test_u2prim_prim2u_round_trip_and_floors():
+    o = Oracle(_par(SOLVER_HLLD, True))
+    for w in _states(8, 32, 4):
+        u = o.prim2u(w)
+        w2, T = o.u2prim(u)
+        assert np.abs(w2 - w).max() <= 4e-15 * (np.abs(w).max() + 1)
+        assert abs(T - w[4] / w[0] * o.p.Tempsc) <= 1e-14 * T
+    w, _ = o.u2prim(np.array([0.0, 0, 0, 0, -1.0, 0, 0, 0]))           # floors: hydro_core.f90:62,78
+    assert w[0] == 1e-15 and w[4] == 1e-16
+
+
+def test_wave_speeds():
+    o = Oracle(_par(SOLVER_HLLD, True))
+    g = o.p.gamma
+    assert o.csound(2.0, 3.0) == np.sqrt(g * 2.0 / 3.0)
+    w = np.array([1.3, 0.1, 0.2, 0.3, 0.7, 0.0, 0.4, 0.5])             # Bx = 0: cf^2 = (gamma p + B^2)/rho
+    assert abs(o.cfastX(w) - np.sqrt((g * 0.7 + 0.41) / 1.3)) < 1e-15
+    w[5], w[6], w[7] = 0.9, 0.0, 0.0                                   # field-aligned: max(a, v_A)
+    assert abs(o.cfastX(w) - max(np.sqrt(g * 0.7 / 1.3), 0.9 / np.sqrt(1.3))) < 1e-14
+    c = o.cfast(0.7, 1.3, 0.9, 0.4, 0.5)
+    for ax, bn in enumerate((0.9, 0.4, 0.5)):
+        ww = np.array([1.3, 0, 0, 0, 0.7, bn, 0, 0]); ww[6] = np.sqrt(0.9 ** 2 + 0.4 ** 2 + 0.5 ** 2 - bn ** 2)
+        assert abs(c[ax] - o.cfastX(ww)) < 1e-14
+
+
+# ---- KAT 2: uniform state is a fixed point of tstep, bitwise ------------------------------
+@pytest.mark.parametrize("solver,mhd", SOLVERS)
+@pytest.mark.parametrize("bc", [None, BC_OUTFLOW, BC_CLOSED])
+def test_uniform_state_is_a_fixed_point(solver, mhd, bc):
+    kw = dict(enable_flux_cd=mhd)
+    if bc is not None:
+        kw.update(bc_left=bc, bc_right=bc, bc_bottom=bc, bc_top=bc, bc_out=bc, bc_in=bc)
+    p = _par(solver, mhd, nxtot=8, nytot=6, nztot=4, **kw)
+    o = Oracle(p)
+    w = np.array([1.1, 0.0, 0.0, 0.0, 0.8, 0.3, -0.2, 0.5][:p.neq])
+    if bc is None:
+        w[1:4] = (0.3, -0.2, 0.1)                                     # a moving uniform state is only steady without walls
+    u = o.prim2u(w)
+    g = np.zeros(p.block_shape(), order="F")
+    g[...] = u[:, None, None, None]
+    o.scatter_u(g); o.start()
+    o.advance(3)
+    assert np.array_equal(o.get_block(0, U)[..., 2:-2, 2:-2, 2:-2], g[..., 2:-2, 2:-2, 2:-2])
+
+
+# ---- KAT 3: x / y / z equivalence (swapy / swapz, src/hydro_core.f90:485-534) -------------
+@pytest.mark.parametrize("solver,mhd", [(SOLVER_HLLD, True), (SOLVER_HLLC, False)])
+def test_one_dimensional_problem_is_identical_along_every_axis(solver, mhd):
+    n = 48
+
+    def run(axis):
+        dims = [2, 2, 2]; dims[axis] = n
+        ext = [2.0 / n] * 3; ext[axis] = 1.0
+        p = Params(nxtot=dims[0], nytot=dims[1], nztot=dims[2], xmax=ext[0], ymax=ext[1], zmax=ext[2], mhd=mhd,
+                   riemann_solver=solver, enable_flux_cd=False, cfl=0.4)
+        s = (np.arange(-1, n + 3) - 0.5) / n
+        rho = 1.0 + 0.3 * np.sin(2 * np.pi * s); pr = 1.0 + 0.2 * np.cos(2 * np.pi * s)
+        vn = 0.4 * np.sin(4 * np.pi * s); vt = 0.3 * np.cos(2 * np.pi * s)
+        bn = 0.5 + 0 * s; bt = 0.4 * np.sin(2 * np.pi * s)
+        shape = [1, 1, 1]; shape[axis] = n + 4
+        R = lambda a: a.reshape(shape)
+        t1 = (axis + 1) % 3
+        v = [0 * R(s)] * 3; b = [0 * R(s)] * 3
+        v[axis] = R(vn); v[t1] = R(vt); b[axis] = R(bn); b[t1] = R(bt)
+        g = np.zeros(p.block_shape(), order="F")
+        g[0] = R(rho); g[1] = R(rho) * v[0]; g[2] = R(rho) * v[1]; g[3] = R(rho) * v[2]
+        e = 0.5 * R(rho) * (v[0] ** 2 + v[1] ** 2 + v[2] ** 2) + p.cv * R(pr)
+        if mhd:
+            e = e + 0.5 * (b[0] ** 2 + b[1] ** 2 + b[2] ** 2)
+            g[5] = b[0]; g[6] = b[1]; g[7] = b[2]
+        g[4] = e
+        o = oracle_from_ic(p, g, threads=1)
+        o.advance(12)
+        u = o.get_block(0, U)[..., 2:-2, 2:-2, 2:-2]
+        line = np.moveaxis(u, 1 + axis, 1)[:, :, 0, 0]
+        # rotate components back to (normal, t1, t2)
+        t2 = (axis + 2) % 3
+        perm = [0, 1 + axis, 1 + t1, 1 + t2, 4] + ([5 + axis, 5 + t1, 5 + t2] if mhd else [])
+        return line[perm]
+    x, y, z = run(0), run(1), run(2)
+    assert np.array_equal(x, y) and np.array_equal(x, z)
+
+
+# ---- KAT 5: conservation and div B on a periodic box -------------------------------------
+def _divb(u, p):
+    bx, by, bz = u[5], u[6], u[7]
+    return ((np.roll(bx, -1, 0) - np.roll(bx, 1, 0)) / (2 * p.dx) + (np.roll(by, -1, 1) - np.roll(by, 1, 1)) / (2 * p.dy)
+            + (np.roll(bz, -1, 2) - np.roll(bz, 1, 2)) / (2 * p.dz))
+
+
+@pytest.mark.parametrize("cd", [True, False])
+def test_periodic_box_conserves_and_flux_cd_keeps_divB(cd):
+    p = Params(nxtot=20, nytot=16, nztot=12, zmax=1.0, enable_flux_cd=cd)
+    g = global_ic(p, "random")
+    o = oracle_from_ic(p, g, threads=2)
+    u0 = o.gather(U)
+    o.advance(6)
+    u1 = o.gather(U)
+    for q in range(5 if not cd else 8):       # without cleaning B_n fluxes are not telescoping for B_n (ff(6)=0 only)
+        s0, s1 = u0[q].sum(), u1[q].sum()
+        assert abs(s1 - s0) <= 1e-12 * np.abs(u0[q]).sum(), (q, s0, s1)
+    d0, d1 = _divb(u0, p), _divb(u1, p)       # Out_BIN_Module.f90:217-219 central-difference div B
+    if cd:
+        assert np.abs(d1 - d0).max() <= 1e-11 * (np.abs(u0[5:8]).max() / p.dx)
+    else:
+        assert np.abs(d1 - d0).max() > 1e-8   # the uncleaned scheme does change div B (sanity of the test itself)
+
+
+# ---- KAT 6: Orszag-Tang keeps its 180-degree rotational symmetry ------------------------
+def test_orszag_tang_point_symmetry():
+    """The OT initial condition (OT/orzag_tang.f90:40-45) is invariant under (x,y) -> (1-x,1-y),
+    (v,B) -> (-v,-B); the scheme preserves that.  Cell centres of the reference sit at (i+0.5)dx
+    (offset by one cell), so the mirror image of (1-based) cell i is cell n-1-i, periodically wrapped."""
+    n = 32
+    p = Params(nxtot=n, nytot=n, nztot=2, zmax=2.0 / n)
+    o = oracle_from_ic(p, global_ic(p, "ot"), threads=2)
+    o.advance(12)
+    u = o.gather(U)[:, :, :, 0]
+    idx = (n - 3 - np.arange(n)) % n          # 0-based image of cell a
+    m = u[:, idx][:, :, idx]
+    sgn = np.array([1, -1, -1, -1, 1, -1, -1, -1.0])[:, None, None]
+    assert np.abs(m * sgn - u).max() <= 1e-12 * np.abs(u).max()
+    rho = u[0]
+    assert 0.05 < rho.min() and rho.max() < 0.5      # colour range OT/plots.py:27 uses for rho
+
+
+# ---- KAT 7: invariance under the block decomposition (Q1/Q2) ----------------------------
+@pytest.mark.parametrize("nb", [(4, 1, 1), (1, 2, 2), (2, 2, 2)])
+@pytest.mark.parametrize("problem,kw", [("random", {}), ("blast", dict(bc_left=BC_OUTFLOW, bc_right=BC_OUTFLOW, bc_out=BC_CLOSED, bc_in=BC_CLOSED))])
+def test_block_decomposition_does_not_change_the_interior(nb, problem, kw):
+    p1 = Params(nxtot=16, nytot=12, nztot=8, zmax=1.0, **kw)
+    g = global_ic(p1, problem, **({"r0": 0.3} if problem == "blast" else {}))
+    a = oracle_from_ic(p1, g, threads=1)
+    b = oracle_from_ic(p1.replace(MPI_NBX=nb[0], MPI_NBY=nb[1], MPI_NBZ=nb[2]), g, threads=4)
+    assert b.nblocks == nb[0] * nb[1] * nb[2]
+    da, db = a.advance(4), b.advance(4)
+    assert da == db
+    assert np.array_equal(a.gather(U), b.gather(U))
+    assert np.array_equal(a.gather(UP), b.gather(UP))
+
+
+def test_rank_coordinate_map_is_row_major():
+    """rank = (cx*NBY + cy)*NBZ + cz (py/guacho_utils.py:104-118) and mpi_cart_shift neighbours."""
+    from guacho_b200.decomp import coords_of, rank_of, neighbors
+    p = Params(nxtot=8, nytot=8, nztot=8, zmax=1.0, MPI_NBX=2, MPI_NBY=2, MPI_NBZ=2, bc_left=BC_OUTFLOW, bc_right=BC_OUTFLOW)
+    o = Oracle(p)
+    for r in range(8):
+        c = o.coords(r)
+        assert c == coords_of(r, (2, 2, 2)) and rank_of(c, (2, 2, 2)) == r
+        assert o.neighbors(r) == neighbors(p, c)
