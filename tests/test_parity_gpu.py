@@ -75,3 +75,60 @@ def test_eight_wave_and_viscosity_and_passives():
     p = Params(nxtot=24, nytot=20, nztot=16, zmax=1.0, enable_flux_cd=False, eight_wave=True, eta=0.01, npas=2, strict_fp=True)
     ug, uo, _, _ = run_pair(p, "random", nsteps=3)
     assert rel_err_per_var(ug, uo).max() <= TOL
+
+
+# ---- committed fixtures (tests/golden/, produced by the oracle; no oracle library needed at run time) ----
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("name", ["oracle_ot_hlld_cd_24x20x4", "oracle_random_hlld_cd_16x12x10", "oracle_random_hllc_16x12x10"])
+def test_cuda_path_matches_committed_fixture(name, strict):
+    import os
+    from guacho_b200.solver import Block
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    nx, ny, nz = (int(v) for v in g["params"])
+    kw = dict(nxtot=nx, nytot=ny, nztot=nz, zmax=float(g["zmax"]), strict_fp=strict)
+    if "hllc" in name:
+        kw.update(mhd=False, riemann_solver=SOLVER_HLLC, enable_flux_cd=False)
+    with Block(Params(**kw)) as b:
+        b.set_state(g["u0"])
+        t, it = 0.0, 1
+        for dt_ref in g["dts"]:
+            dt, _ = b.get_timestep(it, 10, t, 1e300)
+            assert abs(dt - dt_ref) <= 1e-13 * dt_ref
+            b.tstep(float(dt_ref))
+            t += float(dt_ref); it += 1
+        u = interior(b.get_state())
+    err = rel_err_per_var(u, g["u"])
+    assert err.max() <= (1e-15 if strict else TOL), err
+
+
+# ---- BASELINE.json configs[1] at full size: size-independent properties ----
+def test_full_size_256_cubed_properties():
+    """3-D Orszag-Tang 256^3, HLLD + flux-CD (the bench workload), 4 steps on the production kernels:
+    mass/momentum/energy/B sums conserved to round-off, central-difference div B unchanged (flux-CD),
+    the 180-degree point symmetry of the OT field kept, z-invariance kept bitwise, and the strict
+    and fast kernels agree to the parity tolerance."""
+    from guacho_b200.solver import Block
+    from guacho_b200.config import ot_3d
+    n = 256
+    out = {}
+    for strict in (False, True):
+        p = ot_3d(n, strict_fp=strict)
+        g = global_ic(p, "ot")
+        with Block(p) as b:
+            b.set_state(g)
+            t, it, _ = b.run(4, 0.0, 1)
+            u = interior(b.get_state())
+        out[strict] = u
+        u0 = interior(g)
+        for q in range(8):
+            assert abs(u[q].sum() - u0[q].sum()) <= 1e-11 * np.abs(u0[q]).sum(), q
+        def divb(a):
+            return ((np.roll(a[5], -1, 0) - np.roll(a[5], 1, 0)) / (2 * p.dx) + (np.roll(a[6], -1, 1) - np.roll(a[6], 1, 1)) / (2 * p.dy)
+                    + (np.roll(a[7], -1, 2) - np.roll(a[7], 1, 2)) / (2 * p.dz))
+        assert np.abs(divb(u) - divb(u0)).max() <= 1e-10 * np.abs(u0[5:8]).max() / p.dx
+        assert np.array_equal(u[..., 0], u[..., n // 2]) and np.array_equal(u[..., 0], u[..., n - 1])     # z-invariant input stays z-invariant
+        s = u[..., 0]
+        idx = (n - 3 - np.arange(n)) % n
+        sgn = np.array([1, -1, -1, -1, 1, -1, -1, -1.0])[:, None, None]
+        assert np.abs(s[:, idx][:, :, idx] * sgn - s).max() <= 1e-11 * np.abs(s).max()
+    assert rel_err_per_var(out[False], out[True]).max() <= TOL
