@@ -14,6 +14,7 @@ from dataclasses import dataclass, field, asdict
 SOLVER_HLL, SOLVER_HLLC, SOLVER_HLLE, SOLVER_HLLD = 1, 2, 3, 4
 EOS_ADIABATIC, EOS_SINGLE_SPECIE, EOS_H_RATE, EOS_CHEM = 1, 2, 3, 4
 BC_OUTFLOW, BC_CLOSED, BC_PERIODIC, BC_OTHER = 1, 2, 3, 4
+COOL_NONE, COOL_H = 0, 1
 LIMITER_NO_AVERAGE, LIMITER_NO_LIMIT, LIMITER_MINMOD, LIMITER_VAN_LEER = -1, 0, 1, 2
 LIMITER_VAN_ALBADA, LIMITER_UMIST, LIMITER_WOODWARD, LIMITER_SUPERBEE = 3, 4, 5, 6
 
@@ -38,10 +39,10 @@ class GxConfig(C.Structure):
         ("enable_flux_cd", C.c_int32), ("eight_wave", C.c_int32), ("user_source_terms", C.c_int32),
         ("bc_left", C.c_int32), ("bc_right", C.c_int32), ("bc_bottom", C.c_int32),
         ("bc_top", C.c_int32), ("bc_out", C.c_int32), ("bc_in", C.c_int32),
-        ("bc_user", C.c_int32), ("strict_fp", C.c_int32), ("reserved0", C.c_int32),
+        ("bc_user", C.c_int32), ("strict_fp", C.c_int32), ("cooling", C.c_int32),
         ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double),
         ("cv", C.c_double), ("gamma", C.c_double), ("Tempsc", C.c_double),
-        ("cfl", C.c_double), ("eta", C.c_double),
+        ("cfl", C.c_double), ("eta", C.c_double), ("tsc", C.c_double),
     ]
 
 
@@ -77,6 +78,8 @@ class Params:
     Tempsc: float = 1.0
     cfl: float = 0.2
     eta: float = 0.0
+    cooling: int = COOL_NONE
+    tsc: float = 1.0
     tmax: float = 0.5
     dtprint: float = 0.1
     strict_fp: bool = False
@@ -146,6 +149,8 @@ class Params:
             raise ValueError("HLLE/HLLD need mhd=True (they use cfastX)")
         if self.riemann_solver in (SOLVER_HLL, SOLVER_HLLC) and self.mhd:
             raise ValueError("HLL/HLLC use the hydro sound speed: run them with mhd=False")
+        if self.cooling == COOL_H and self.npas < 1:
+            raise ValueError("COOL_H evolves the neutral-H passive u(neqdyn+1): needs npas >= 1 (cooling_h.f90:30)")
         if self.enable_flux_cd and not self.mhd:
             raise ValueError("flux-CD without B field updates nothing (hydro_solver.f90:103-113)")
 
@@ -169,6 +174,7 @@ class Params:
         c.dx, c.dy, c.dz = self.dx, self.dy, self.dz
         c.cv, c.gamma, c.Tempsc = self.cv, self.gamma, self.Tempsc
         c.cfl, c.eta = self.cfl, self.eta
+        c.cooling, c.tsc = self.cooling, self.tsc
         return c
 
     def replace(self, **kw) -> "Params":

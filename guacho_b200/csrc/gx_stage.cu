@@ -61,16 +61,16 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // as late as the data dependence allows, by a parity wait.  All NT threads arrive once per
 // plane on each barrier; phase parity = plane counter & 1.
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-  asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "MBAR_WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@!p bra MBAR_WAIT_%=;\n\t}"
       ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }

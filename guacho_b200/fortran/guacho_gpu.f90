@@ -26,8 +26,8 @@ module guacho_gpu
     integer(c_int32_t) :: riemann_solver, slope_limiter, eq_of_state
     integer(c_int32_t) :: enable_flux_cd, eight_wave, user_source_terms
     integer(c_int32_t) :: bc_left, bc_right, bc_bottom, bc_top, bc_out, bc_in
-    integer(c_int32_t) :: bc_user, strict_fp, reserved0
-    real(c_double)     :: dx, dy, dz, cv, gamma, Tempsc, cfl, eta
+    integer(c_int32_t) :: bc_user, strict_fp, cooling
+    real(c_double)     :: dx, dy, dz, cv, gamma, Tempsc, cfl, eta, tsc
   end type gx_config
 
   type(c_ptr), save :: gx_handle = c_null_ptr   !< the solver of this MPI rank
@@ -134,9 +134,10 @@ contains
     c%bc_left = bc_left; c%bc_right = bc_right; c%bc_bottom = bc_bottom
     c%bc_top = bc_top;   c%bc_out = bc_out;     c%bc_in = bc_in
     c%bc_user = merge(1, 0, bc_user)
-    c%strict_fp = 0; c%reserved0 = 0
+    c%strict_fp = 0
+    c%cooling = merge(cooling, 0, cooling == COOL_H)   ! the other cooling modules stay in the host
     c%dx = dx; c%dy = dy; c%dz = dz
-    c%cv = cv; c%gamma = gamma; c%Tempsc = Tempsc; c%cfl = cfl; c%eta = eta
+    c%cv = cv; c%gamma = gamma; c%Tempsc = Tempsc; c%cfl = cfl; c%eta = eta; c%tsc = tsc
     call gx_check(gx_create(c, gx_handle), 'gx_create')
   end subroutine gx_initmain
 

@@ -21,7 +21,7 @@ ERRORS = {-1: "GX_EINVAL", -2: "GX_ENODEVICE", -3: "GX_ECUDA", -4: "GX_ENOMEM",
 # every symbol include/guacho_gx.h declares (checked by tests/test_abi.py)
 EXPORTS = (
     "gx_create", "gx_destroy", "gx_set_state", "gx_set_time", "gx_get_timestep", "gx_tstep", "gx_run",
-    "gx_get_state", "gx_get_up", "gx_set_gravity_points", "gx_set_wind_spheres", "gx_register_host_bc",
+    "gx_get_state", "gx_get_up", "gx_set_gravity_points", "gx_set_wind_spheres", "gx_register_host_bc", "gx_register_bc_hook",
     "gx_comm_unique_id", "gx_comm_attach", "gx_last_error", "gx_launch_count", "gx_last_elapsed_ms",
     "gx_kernel_time_ms", "gx_set_profiling", "gx_build_info",
 )
@@ -37,12 +37,13 @@ class GxError(RuntimeError):
 
 class WindSphere(C.Structure):
     _fields_ = [("xc", C.c_double), ("yc", C.c_double), ("zc", C.c_double), ("radius", C.c_double),
-                ("vwind", C.c_double), ("dens", C.c_double), ("temp_eff", C.c_double),
+                ("vwind", C.c_double), ("dens", C.c_double), ("tfac", C.c_double), ("temp", C.c_double),
                 ("vbx", C.c_double), ("vby", C.c_double), ("vbz", C.c_double),
                 ("bdip", C.c_double), ("pas", C.c_double * 4)]
 
 
 HOST_BC_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int32, C.c_void_p)
+BC_HOOK_FN = C.CFUNCTYPE(None, C.c_int32, C.c_double, C.c_void_p)
 
 _lib = None
 
@@ -71,6 +72,7 @@ def load() -> C.CDLL:
     L.gx_set_gravity_points.argtypes = [vp, C.c_int32, dp, dp]
     L.gx_set_wind_spheres.argtypes = [vp, C.c_int32, C.POINTER(WindSphere)]
     L.gx_register_host_bc.argtypes = [vp, HOST_BC_FN, vp]
+    L.gx_register_bc_hook.argtypes = [vp, BC_HOOK_FN, vp]
     L.gx_comm_unique_id.argtypes = [vp, C.c_int32]
     L.gx_comm_attach.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32]
     L.gx_last_error.restype = C.c_char_p

@@ -147,6 +147,16 @@ class Block:
         self._host_bc_ref = _lib.HOST_BC_FN(tramp)
         check(self.L.gx_register_host_bc(self.h, self._host_bc_ref, None))
 
+    def register_bc_hook(self, fn: Optional[Callable[[int, float], None]]) -> None:
+        """`fn(order, time)` runs at the top of every impose_user_bc application; it may re-position the
+        device functors (set_wind_spheres / set_gravity_points), like exoplanet.f90:137-144 moves the planet."""
+        if fn is None:
+            self._bc_hook_ref = None
+            check(self.L.gx_register_bc_hook(self.h, _lib.BC_HOOK_FN(0), None))
+            return
+        self._bc_hook_ref = _lib.BC_HOOK_FN(lambda order, time, _user: fn(int(order), float(time)))
+        check(self.L.gx_register_bc_hook(self.h, self._bc_hook_ref, None))
+
     # -- multi-GPU --
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -43,6 +43,8 @@ enum { GX_LIMITER_NO_AVERAGE = -1, GX_LIMITER_NO_LIMIT = 0, GX_LIMITER_MINMOD = 
        GX_LIMITER_VAN_LEER = 2, GX_LIMITER_VAN_ALBADA = 3, GX_LIMITER_UMIST = 4,
        GX_LIMITER_WOODWARD = 5, GX_LIMITER_SUPERBEE = 6 };
 
+enum { GX_COOL_NONE = 0, GX_COOL_H = 1, GX_COOL_BBC = 2, GX_COOL_DMC = 3, GX_COOL_CHI = 4, GX_COOL_CHEM = 5 };
+
 /* ---- error codes ---- */
 enum { GX_OK = 0, GX_EINVAL = -1, GX_ENODEVICE = -2, GX_ECUDA = -3, GX_ENOMEM = -4,
        GX_EUNSUPPORTED = -5, GX_ESTATE = -6, GX_ECOMM = -7, GX_ENUMERIC = -8 };
@@ -68,11 +70,14 @@ typedef struct gx_config {
   int32_t bc_user;
   int32_t strict_fp;         /* 1: kernels built with -fmad=false (bit-comparison mode,
                                 matches the reference's no-FMA x86 build); 0: FMA     */
-  int32_t reserved0;
+  int32_t cooling;           /* GX_COOL_*: NONE, or H = the parametrised hydrogen cooling operator
+                                (src/cooling_h.f90:41-67, applied after viscous_copy, hydro_solver.f90:202-204);
+                                it needs EOS_H_RATE-style passives (npas >= 1: neutral H density)   */
   double dx, dy, dz;         /* globals dx dy dz (src/init.f90:120-122)               */
   double cv, gamma;          /* parameters.f90: cv, gamma=(cv+1)/cv                   */
   double Tempsc;             /* temperature scaling used by u2prim                    */
   double cfl, eta;
+  double tsc;                /* time scaling to seconds (parameters.f90: tsc); used by GX_COOL_H only  */
 } gx_config;
 
 typedef struct gx_solver gx_solver;   /* opaque; one per block (= per GPU / MPI rank) */
@@ -135,14 +140,24 @@ GX_API int gx_set_gravity_points(gx_solver* s, int32_t n, const double* gm, cons
  * Each sphere: centre, radius, radial wind speed, density, thermal term
  * cv*dens*T_eff, bulk velocity, dipole moment amplitude (b0 at radius), passive
  * values per unit density.  See gx_wind_sphere. */
+#define GX_MAX_SPHERES 4
 typedef struct gx_wind_sphere {
   double xc, yc, zc, radius;
-  double vwind, dens, temp_eff;      /* u5 thermal part = cv*dens*temp_eff       */
+  double vwind, dens;
+  double tfac, temp;                 /* u5 thermal part = cv*dens*tfac*temp (EXO: 1|1.9999 x TSW, 1.8 x TPW) */
   double vbx, vby, vbz;              /* bulk (orbital) velocity added to the wind */
   double bdip;                       /* dipole field strength at `radius`        */
   double pas[4];                     /* passive scalars per unit density (npas<=4) */
 } gx_wind_sphere;
 GX_API int gx_set_wind_spheres(gx_solver* s, int32_t n, const gx_wind_sphere* sph);
+
+/* Host hook run at the top of every impose_user_bc application (boundaryI: order 1, boundaryII: order 2;
+ * src/boundaries.f90:245,508) with globals::time as set by gx_set_time.  It exists because the reference's
+ * problem modules mutate their own state there (EXO/exoplanet.f90:137-144 moves the planet, and the user
+ * SOURCE then sees that position, EXO/user_mod.f90:174-187): the hook may call gx_set_wind_spheres /
+ * gx_set_gravity_points, which take effect immediately.  No array crosses the boundary; cheap. */
+typedef void (*gx_bc_hook_fn)(int32_t order, double time, void* user);
+GX_API int gx_register_bc_hook(gx_solver* s, gx_bc_hook_fn cb, void* user);
 
 /* Slow path for arbitrary user code: host callbacks run on a host copy of the
  * array in reference layout (device -> host -> callback -> device). Excluded

@@ -47,6 +47,7 @@ struct Par {
   int bc_left, bc_right, bc_bottom, bc_top, bc_out, bc_in;
   bool bc_user;
   double dx, dy, dz, cv, gamma, Tempsc, cfl, eta;
+  int cooling; double tsc;        // parameters.f90: cooling, tsc
   int nxmin, nxmax, nymin, nymax, nzmin, nzmax;   // parameters.f90:222-227
 };
 
@@ -842,7 +843,109 @@ static void viscous_copy(Oracle& O) {
   });
 }
 
-// src/hydro_solver.f90:134-229 tstep  (hydro/MHD part; operator-split add-ons are out of scope)
+// ---------------------------------------------------------------------------
+// src/cooling_h.f90 — parametrised hydrogen cooling (COOL_H), a cell-local operator applied to u after
+// viscous_copy (src/hydro_solver.f90:202-204).  Arithmetic note: the reference is built with
+// -fdefault-real-8, under which gfortran promotes the `d`-exponent literals below (2.55d-13, 1.d4, 5.83d-11,
+// 1.133D-24, xi, boltzm) to 16-byte reals, so those sub-expressions are evaluated in quad precision and then
+// rounded to real(8).  This restatement evaluates them in FP64: the results agree with the correctly rounded
+// values to an ulp or two, far inside the parity tolerance stated in tests/test_exo_gpu.py.
+static double cool_alpha(double T) { return 2.55e-13 * std::pow(1.e4 / T, 0.79); }                 // cooling_h.f90:75-84
+static double cool_colf(double T) { return 5.83e-11 * std::sqrt(T) * std::exp(-157828. / T); }      // :109-118
+static double cool_betah(double T) {                                                              // :126-137
+  double a = 157890. / T;
+  return 1.133e-24 / std::sqrt(a) * (-0.0713 + 0.5 * std::log(a) + 0.640 * std::pow(a, -0.33333));
+}
+// cooling_h.f90:159-246 ALOSS(X1,X2,DT,DEN,DH0,TE0)
+static double cool_aloss(double X1, double X2, double DT, double DEN, double DH0, double TE0) {
+  const double XION = 2.179e-11, XO = 1.e-3;
+  const double C0 = 0.5732, C1 = 1.8288e-5, C2 = -1.15822e-10, C3 = 9.4288e-16;
+  const double D0 = 0.5856, D1 = 1.55083e-5, D2 = -9.669e-12, D3 = 5.716e-19;
+  const double ENK = 118409., EN = 1.634E-11;
+  double TE = std::max(TE0, 10.);
+  double DH = DEN;
+  double DHP = (1. - X1) * DH;
+  double DE = DHP + 1.E-4 * DH;
+  double DOI = XO * DH0;
+  double DOII = XO * DHP;
+  (void)X2; (void)DT;                                  // SHP is computed but never used (:183)
+  if (TE <= 1e4) return 0.;
+  double OMEGA = 0.;
+  if (TE <= 55000.) OMEGA = C0 + TE * (C1 + TE * (C2 + TE * C3));
+  if (TE >= 72000.) OMEGA = D0 + TE * (D1 + TE * (D2 + TE * D3));
+  if (TE > 55000. && TE < 72000.) {
+    double OMEGAL = C0 + TE * (C1 + TE * (C2 + TE * C3));
+    double OMEGAH = D0 + TE * (D1 + TE * (D2 + TE * D3));
+    double FRAC = (TE - 55000.) / 17000.;
+    OMEGA = (1. - FRAC) * OMEGAL + FRAC * OMEGAH;
+  }
+  double QLA = 8.6287E-6 / (2. * std::sqrt(TE)) * OMEGA * std::exp(-ENK / TE);
+  double ECOLL = DE * DH0 * QLA * EN;
+  ECOLL = std::max(ECOLL, 0.);
+  double CION = 5.834E-11 * std::sqrt(TE) * std::exp(-1.579E5 / TE);
+  double EION = DE * DH0 * CION * XION;
+  double EREC = DE * DHP * (cool_betah(TE));
+  EREC = std::max(EREC, 0.);
+  double TM = 1. / TE;
+  double T2 = TM * TM;
+  double EOI = DE * DOI * std::pow(10., 1381465 * T2 - 12328.69 * TM - 19.82621);
+  double EOII = DE * DOII * std::pow(10., -2061075. * T2 - 14596.24 * TM - 19.01402);
+  EOI = std::max(EOI, 0.);
+  EOII = std::max(EOII, 0.);
+  double BETAF = 1.3 * 1.42E-27 * std::pow(TE, 0.5);
+  double HIICOOL = DE * DHP * BETAF;
+  double EQUIL = (1.0455E-18 / std::pow(TE, 0.63)) * (1. - std::exp(-std::pow(TE * 1.E-5, 1.63))) * DE * DEN + HIICOOL;
+  double FR = 0.;
+  if (TE <= 44770.) FR = 0.;
+  if (TE >= 54770.) FR = 1.;
+  if (TE > 44770. && TE < 54770.) {
+    double EX2 = std::exp(-2. * (TE - 49770.) / 500.);
+    double TANH = (1. - EX2) / (1. + EX2);
+    FR = 0.5 * (1. + TANH);
+  }
+  return ECOLL + EION + (EREC + 7.033 * (EOI + EOII)) * (1. - FR) + EQUIL * FR;
+}
+// cooling_h.f90:259-371 atomic(dt,uu,tau,radphi)  (dif_rad = .false. branch: radphi unused)
+static void cool_atomic(const Par& P, double dt, double* uu) {
+  const double xi = 1.e-4, boltzm = 1.3807e-16;
+  double prim[16], T;
+  u2prim(P, uu, prim, T);
+  double col = cool_colf(T);
+  double rec = cool_alpha(T);
+  double y0 = uu[P.neqdyn] / uu[0];
+  double dh = uu[0];
+  double a = rec + col;
+  double b = -((2. + xi) * rec + (1. + xi) * col);
+  double c = (1. + xi) * rec;
+  double d = std::sqrt(b * b - 4. * a * c);
+  double g0 = (2. * a * y0 + b + d) / (2. * a * y0 + b - d);
+  double e = std::exp(-d * dh * dt);
+  double y1 = (-b - d * (1. + g0 * e) / (1. - g0 * e)) / (2. * a);
+  y1 = std::min(y1, 0.9999);
+  y1 = std::max(y1, 0.);
+  double dh0 = uu[P.neqdyn];
+  double al = cool_aloss(y0, y1, dt, dh, dh0, T) / (dh * dh);
+  double tprime = 10.;
+  double ce = (2. * dh * al) / (3. * boltzm * T);
+  double t1 = tprime + (T - tprime) * std::exp(-ce * dt);
+  t1 = std::max(t1, 0.1 * T);
+  t1 = std::min(t1, 10. * T);
+  uu[P.neqdyn] = y1 * uu[0];
+  if (P.mhd) uu[4] = P.cv * (2. * uu[0] - uu[P.neqdyn]) * t1 / P.Tempsc + 0.5 * prim[0] * (prim[1] * prim[1] + prim[2] * prim[2] + prim[3] * prim[3])
+                     + 0.5 * (prim[5] * prim[5] + prim[6] * prim[6] + prim[7] * prim[7]);
+  else uu[4] = P.cv * (2. * uu[0] - uu[P.neqdyn]) * t1 / P.Tempsc + 0.5 * prim[0] * (prim[1] * prim[1] + prim[2] * prim[2] + prim[3] * prim[3]);
+}
+// cooling_h.f90:41-67 coolingh
+static void coolingh(Oracle& O, double dt_CFL) {
+  const Par& P = O.P;
+  const double dt_seconds = dt_CFL * P.tsc;
+  for_blocks(O, [&](Block& b) {
+    for (int k = 1; k <= P.nz; ++k) for (int j = 1; j <= P.ny; ++j) for (int i = 1; i <= P.nx; ++i)
+      cool_atomic(P, dt_seconds, b.u.cell(i, j, k));
+  });
+}
+
+// src/hydro_solver.f90:134-229 tstep  (hydro/MHD part + COOL_H; the other operator-split add-ons are out of scope)
 static int tstep(Oracle& O, double dt_CFL) {
   const Par& P = O.P;
   std::atomic<int> err(0);
@@ -854,6 +957,7 @@ static int tstep(Oracle& O, double dt_CFL) {
   for_blocks(O, [&](Block& b) { err |= fluxes(P, b, 2); });             // :174-180
   step(O, dt_CFL);                                                      // :184
   viscous_copy(O);                                                      // :188
+  if (P.cooling == GX_COOL_H) coolingh(O, dt_CFL);                      // :202-204
   boundaryI(O);                                                         // :216
   for_blocks(O, [&](Block& b) { calcprim(P, b.u, b.primit, b.Temp); }); // :218-220 (cooling NONE/H branch)
   if (err) O.error_flag = true;
@@ -1054,6 +1158,7 @@ static Oracle* create(const gx_config& c) {
   P.bc_left = c.bc_left; P.bc_right = c.bc_right; P.bc_bottom = c.bc_bottom; P.bc_top = c.bc_top; P.bc_out = c.bc_out; P.bc_in = c.bc_in;
   P.bc_user = c.bc_user;
   P.dx = c.dx; P.dy = c.dy; P.dz = c.dz; P.cv = c.cv; P.gamma = c.gamma; P.Tempsc = c.Tempsc; P.cfl = c.cfl; P.eta = c.eta;
+  P.cooling = c.cooling; P.tsc = c.tsc;
   P.nxmin = -1; P.nxmax = P.nx + 2; P.nymin = -1; P.nymax = P.ny + 2; P.nzmin = -1; P.nzmax = P.nz + 2;
   const bool perx = (P.bc_left == GX_BC_PERIODIC && P.bc_right == GX_BC_PERIODIC);    // src/init.f90:64-66
   const bool pery = (P.bc_bottom == GX_BC_PERIODIC && P.bc_top == GX_BC_PERIODIC);
@@ -1197,6 +1302,9 @@ void orc_limiter(void* h, const double* pll, double* pl, double* pr, const doubl
 double orc_average(int slope_limiter, double a, double b) { return orc::average(slope_limiter, a, b); }
 void orc_cfast(void* h, double p, double d, double bx, double by, double bz, double* c3) { orc::cfast(((Oracle*)h)->P, p, d, bx, by, bz, c3[0], c3[1], c3[2]); }
 double orc_cfastX(void* h, const double* prim) { return orc::cfastX(((Oracle*)h)->P, prim); }
+void orc_cool_atomic(void* h, double dt_seconds, double* uu) { orc::cool_atomic(((Oracle*)h)->P, dt_seconds, uu); }
+double orc_cool_rate(int which, double T) { return which == 0 ? orc::cool_alpha(T) : which == 1 ? orc::cool_colf(T) : orc::cool_betah(T); }
+double orc_cool_aloss(double x1, double x2, double dt, double den, double dh0, double te) { return orc::cool_aloss(x1, x2, dt, den, dh0, te); }
 double orc_csound(void* h, double p, double d) { return orc::csound(((Oracle*)h)->P, p, d); }
 
 }  // extern "C"

@@ -84,6 +84,11 @@ def load(fast: bool = False):
     L.orc_cfastX.argtypes = [C.c_void_p, dp]
     L.orc_csound.restype = C.c_double
     L.orc_csound.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    L.orc_cool_atomic.argtypes = [C.c_void_p, C.c_double, dp]
+    L.orc_cool_rate.restype = C.c_double
+    L.orc_cool_rate.argtypes = [C.c_int, C.c_double]
+    L.orc_cool_aloss.restype = C.c_double
+    L.orc_cool_aloss.argtypes = [C.c_double] * 6
     _libs[name] = L
     return L
 
@@ -245,6 +250,12 @@ class Oracle:
 
     def cfastX(self, prim):
         return self.L.orc_cfastX(self.h, _dp(self._vec(prim)))
+
+    def cool_atomic(self, dt_seconds, uu):
+        """atomic(dt, uu, 1., 1.) of src/cooling_h.f90:259-371 on one cell -> new uu."""
+        a = self._vec(uu)
+        self.L.orc_cool_atomic(self.h, dt_seconds, _dp(a))
+        return a[:self.p.neq].copy()
 
     def csound(self, p, d):
         return self.L.orc_csound(self.h, p, d)

@@ -34,8 +34,8 @@ def test_binding_loads_and_reports_build():
 
 
 def test_config_struct_matches_header_size():
-    # all int32 first (33 of them + 1 pad to 8-byte alignment), then 8 doubles
-    assert C.sizeof(GxConfig) == 34 * 4 + 8 * 8
+    # all int32 first (34 of them), then 9 doubles
+    assert C.sizeof(GxConfig) == 34 * 4 + 9 * 8
     c = Params().to_c()
     assert c.struct_bytes == C.sizeof(GxConfig)
 

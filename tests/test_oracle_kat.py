@@ -254,3 +254,60 @@ def test_rank_coordinate_map_is_row_major():
         c = o.coords(r)
         assert c == coords_of(r, (2, 2, 2)) and rank_of(c, (2, 2, 2)) == r
         assert o.neighbors(r) == neighbors(p, c)
+
+
+# ---- COOL_H operator (src/cooling_h.f90), SURVEY 8(f) N1 ---------------------------------
+def _cool_par():
+    from guacho_b200.config import EOS_H_RATE, COOL_H
+    return Params(nxtot=8, nytot=8, nztot=8, zmax=1.0, npas=2, eq_of_state=EOS_H_RATE, cooling=COOL_H, Tempsc=1.0e4 * 5.0 / 3.0,
+                  tsc=3.8e5, enable_flux_cd=False)
+
+
+def test_cooling_rates_known_values():
+    L = load()
+    assert abs(L.orc_cool_rate(0, 1.0e4) - 2.55e-13) < 1e-27                      # alpha(1e4 K), cooling_h.f90:82
+    assert abs(L.orc_cool_rate(0, 1.0e5) / (2.55e-13 * 10 ** -0.79) - 1) < 1e-14
+    T = 2.0e4
+    assert abs(L.orc_cool_rate(1, T) / (5.83e-11 * np.sqrt(T) * np.exp(-157828.0 / T)) - 1) < 1e-14      # colf, :116
+    a = 157890.0 / T
+    assert abs(L.orc_cool_rate(2, T) / (1.133e-24 / np.sqrt(a) * (-0.0713 + 0.5 * np.log(a) + 0.640 * a ** -0.33333)) - 1) < 1e-14
+    assert L.orc_cool_aloss(0.5, 0.5, 1.0, 10.0, 5.0, 9.0e3) == 0.0               # no losses at or below 1e4 K (:184-187)
+    lo, hi = L.orc_cool_aloss(0.5, 0.5, 1.0, 10.0, 5.0, 4.0e4), L.orc_cool_aloss(0.5, 0.5, 1.0, 10.0, 5.0, 6.0e4)
+    assert 0 < lo < hi
+    # continuity across the two blended temperature windows (:190-196, :233-240)
+    for Tb in (55000.0, 72000.0, 44770.0, 54770.0):
+        f0, f1 = L.orc_cool_aloss(0.3, 0.3, 1.0, 1e3, 3e2, Tb * (1 - 1e-9)), L.orc_cool_aloss(0.3, 0.3, 1.0, 1e3, 3e2, Tb * (1 + 1e-9))
+        assert abs(f1 / f0 - 1) < 1e-5, Tb
+
+
+def test_cooling_atomic_cell_properties():
+    p = _cool_par()
+    o = Oracle(p)
+    rng = np.random.default_rng(7)
+    for _ in range(32):
+        n = 10 ** rng.uniform(3, 7)
+        y0 = rng.uniform(0.01, 0.99)
+        T = 10 ** rng.uniform(3.5, 6.2)
+        v = rng.normal(0, 1.0, 3)
+        B = rng.normal(0, 30.0, 3)
+        u = np.zeros(10)
+        u[0] = n; u[1:4] = n * v; u[5:8] = B; u[8] = y0 * n; u[9] = n
+        u[4] = p.cv * (2 * n - u[8]) * T / p.Tempsc + 0.5 * n * (v @ v) + 0.5 * (B @ B)       # cooling_h.f90:353-356 inverted
+        w, T0 = o.u2prim(u)
+        assert abs(T0 / T - 1) < 1e-10
+        for dt in (1.0e2, 1.0e6):
+            u1 = o.cool_atomic(dt, u)
+            assert np.array_equal(u1[[0, 1, 2, 3, 5, 6, 7, 9]], u[[0, 1, 2, 3, 5, 6, 7, 9]])   # only energy and neutral H change
+            y1 = u1[8] / u1[0]
+            assert 0.0 <= y1 <= 0.9999
+            w1, T1 = o.u2prim(u1)
+            assert 0.1 * T0 * (1 - 1e-12) <= T1 <= 10 * T0 * (1 + 1e-12)                       # :340-341 clamps
+            if T0 > 1.0e4:
+                assert T1 <= T0 * (1 + 1e-12)                                                   # losses only (tprime = 10 K)
+        # long time step -> ionisation equilibrium: root of a y^2 + b y + c = 0 (:300-313)
+        L = load()
+        rec, col = L.orc_cool_rate(0, T0), L.orc_cool_rate(1, T0)
+        a, b, c = rec + col, -((2 + 1e-4) * rec + (1 + 1e-4) * col), (1 + 1e-4) * rec
+        yeq = (-b - np.sqrt(b * b - 4 * a * c)) / (2 * a)
+        u_eq = o.cool_atomic(1.0e15, u)
+        assert abs(u_eq[8] / u_eq[0] - min(yeq, 0.9999)) < 1e-9
