@@ -135,7 +135,8 @@ def test_full_size_256_cubed_properties():
 
 
 # ---- full Orszag-Tang run (north_star: "within a stated L1 tolerance over a full Orszag-Tang run") ----
-OT_FULL_L1_TOL = 1e-9      # stated tolerance, relative L1 per conserved variable at t = 0.5 (measured drift: see DESIGN.md §4)
+OT_FULL_L1_TOL = 1e-11     # stated tolerance, relative L1 per conserved variable at t = 0.5; measured on B200: <= 9.2e-13
+                           # over 1635 steps (production FMA/shared-reciprocal kernels vs the no-FMA oracle), DESIGN.md §4
 
 
 def test_full_orszag_tang_run_L1():
