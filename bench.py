@@ -106,9 +106,11 @@ class ClockSampler:
         return out
 
 
-def workload(n_per_gpu: int, world: int) -> Params:
-    # weak scaling: the same n^3 block per GPU, stacked along z
-    return ot_3d(n_per_gpu, nztot=n_per_gpu * world, zmax=1.0 * world)
+def workload(n: int, world: int, strong: bool = False) -> Params:
+    if strong:   # strong scaling: n^3 in total, z-slabs of n/world planes (BASELINE configs[2] "512^3 ... strong")
+        return ot_3d(n)
+    # weak scaling (default): the same n^3 block per GPU, stacked along z
+    return ot_3d(n, nztot=n * world, zmax=1.0 * world)
 
 
 def cpu_reference(p_block: Params, steps: int, warmup: int, threads: int):
@@ -156,10 +158,11 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=256, help="cells per side of the per-GPU block")
+    ap.add_argument("--grid", dest="n", type=int, default=256, help="cells per side of the per-GPU block (with --strong: of the whole domain)")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strict", action="store_true", help="use the -fmad=false bit-comparison kernels")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: --n is the TOTAL grid side, split into z-slabs over the GPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -177,7 +180,9 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
 
-    p = workload(args.n, world).replace(strict_fp=args.strict)
+    if args.strong and args.n % world:
+        raise SystemExit(f"--strong: {args.n} planes do not split over {world} GPUs")
+    p = workload(args.n, world, args.strong).replace(strict_fp=args.strict)
     nb = (1, 1, world)
     blk = make_rank_block(p, rank, world, local_rank, nb=nb)
     pb = blk.p
@@ -305,8 +310,8 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"3-D Orszag-Tang {args.n}^3 per GPU (BASELINE configs[1]), HLLD + flux-CD, minmod, periodic, cfl 0.2",
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": (f"3-D Orszag-Tang {args.n}^3 in total (BASELINE configs[2], strong scaling)" if args.strong else f"3-D Orszag-Tang {args.n}^3 per GPU (BASELINE configs[1])") + ", HLLD + flux-CD, minmod, periodic, cfl 0.2",
                    "grid_total": [pb.nxtot, pb.nytot, pb.nztot], "blocks": list(nb), "neq": pb.neq,
                    "kernels": "strict (-fmad=false)" if args.strict else "fast (-fmad=true)",
                    "l2": "working set (u, up, E: 2.7 GB per GPU at 256^3) exceeds the 126 MB L2; no flush needed",

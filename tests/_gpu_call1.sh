@@ -17,4 +17,4 @@ for lib in guacho_b200/libguacho_gx.so guacho_b200/variants/*.so; do
   GUACHO_GX_LIB=$PWD/$lib python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-steps 0 2>&1 | python -c "$fmt"
 done
 echo "=== 512^3 baseline"
-python bench.py --n 512 --steps 8 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/bench_512.json 2>&1; python -c "$fmt" < gpurun_out/bench_512.json
+python bench.py --grid 512 --steps 8 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/bench_512.json 2>&1; python -c "$fmt" < gpurun_out/bench_512.json
