@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdarg.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -85,6 +86,11 @@ struct gx_solver {
   int bc[3][2];
   // comm
   ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
+  // peer-memory halo push for z slabs (CUDA IPC mappings of the neighbours' arrays over NVLink)
+  bool p2p = false;
+  uint32_t* flags = nullptr;                                  // device: READY/ARRIVE words written by the neighbours
+  struct Peer { double *U = nullptr, *UP = nullptr, *E = nullptr; uint32_t* flags = nullptr; } peer[2];   // [lo, hi]
+  uint32_t xseq = 0;                                          // exchange sequence number (same on every rank)
   // user functors
   std::vector<gx_wind_sphere> spheres;                        // passed to k_wind_spheres by value (<= GX_MAX_SPHERES)
   gx_host_bc_fn host_bc = nullptr; void* host_bc_user = nullptr;
@@ -372,12 +378,68 @@ static void launch_pack(gx_solver* s, int nvar, double* A, double* buf, const Bo
   k_pack<<<grid, 64, 0, s->stream>>>(s->A.g, nvar, A, buf, b, unpack);
 }
 
+// ---- peer-memory halo push (z slabs): replaces pack -> ncclSend/ncclRecv -> unpack ----
+// In the SoA layout the nl boundary planes of one variable are one contiguous run and so are the neighbour's
+// ghost planes, so a z face is ONE strided device-to-device copy (rows = variables, pitch = variable stride)
+// straight into the neighbour's array, mapped here through CUDA IPC: copy engines over NVLink, no kernel, no
+// staging buffer.  Ordering uses stream memory operations on 32-bit words in the RECEIVER's memory:
+//   READY_FROM_x  : written by neighbour x when its stream reaches the exchange ("my ghost planes may be written")
+//   ARRIVE_FROM_x : written by neighbour x after its copy into my ghost planes has completed
+// Every rank first posts READY to both neighbours, then waits for each neighbour's READY before pushing, so the
+// protocol cannot deadlock and a fast rank can never overwrite ghosts its neighbour still reads or re-uploads.
+enum { FL_READY_FROM_LO = 0, FL_READY_FROM_HI = 16, FL_ARRIVE_FROM_LO = 32, FL_ARRIVE_FROM_HI = 48, FL_WORDS = 64 };
+typedef int (*StreamOp32)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+static StreamOp32 g_write32 = nullptr, g_wait32 = nullptr;
+static bool load_stream_memops() {
+  if (g_write32 && g_wait32) return true;
+  cudaDriverEntryPointQueryResult qr;
+  void *w = nullptr, *t = nullptr;
+  if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &w, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) { cudaGetLastError(); return false; }
+  if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &t, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) { cudaGetLastError(); return false; }
+  g_write32 = (StreamOp32)w; g_wait32 = (StreamOp32)t;
+  return true;
+}
+static double* peer_array(const gx_solver* s, int side, const double* A) {
+  return A == s->U ? s->peer[side].U : A == s->UP ? s->peer[side].UP : A == s->E ? s->peer[side].E : nullptr;
+}
+static int exchange_z_p2p(gx_solver* s, double* A, int nvar, int nl) {
+  const Grid& g = s->A.g;
+  const int lo = s->nbr[2][0], hi = s->nbr[2][1];
+  const long long plane = (long long)g.px * g.py;
+  const size_t pitch = (size_t)g.vs * sizeof(double), width = (size_t)nl * plane * sizeof(double);
+  const unsigned seq = ++s->xseq;
+  const unsigned GEQ = 0;                               // CU_STREAM_WAIT_VALUE_GEQ (the words only ever grow)
+  cudaStream_t st = s->stream;
+  auto W = [&](uint32_t* base, int word) { return g_write32(st, (unsigned long long)(uintptr_t)(base + word), seq, 0); };
+  auto T = [&](int word) { return g_wait32(st, (unsigned long long)(uintptr_t)(s->flags + word), seq, GEQ); };
+  int e = 0;
+  if (lo >= 0) e |= W(s->peer[0].flags, FL_READY_FROM_HI);          // I am lo's high neighbour
+  if (hi >= 0) e |= W(s->peer[1].flags, FL_READY_FROM_LO);          // I am hi's low neighbour
+  if (hi >= 0) {                                                    // my top planes nz-nl+1..nz -> hi's ghost planes 1-nl..0
+    e |= T(FL_READY_FROM_HI);
+    CUDA_TRY(cudaMemcpy2DAsync(peer_array(s, 1, A) + (long long)(2 - nl) * plane, pitch, A + (long long)(g.nz - nl + 2) * plane, pitch,
+                               width, (size_t)nvar, cudaMemcpyDeviceToDevice, st));
+    e |= W(s->peer[1].flags, FL_ARRIVE_FROM_LO);
+  }
+  if (lo >= 0) {                                                    // my bottom planes 1..nl -> lo's ghost planes nz+1..nz+nl
+    e |= T(FL_READY_FROM_LO);
+    CUDA_TRY(cudaMemcpy2DAsync(peer_array(s, 0, A) + (long long)(g.nz + 2) * plane, pitch, A + (long long)2 * plane, pitch,
+                               width, (size_t)nvar, cudaMemcpyDeviceToDevice, st));
+    e |= W(s->peer[0].flags, FL_ARRIVE_FROM_HI);
+  }
+  if (lo >= 0) e |= T(FL_ARRIVE_FROM_LO);
+  if (hi >= 0) e |= T(FL_ARRIVE_FROM_HI);
+  if (e) return fail(GX_ECUDA, "stream memory operation failed in the peer halo push (CUresult %d)", e);
+  return GX_OK;
+}
+
 static int exchange_dir(gx_solver* s, double* A, int nvar, int nl, int dir) {
   // all faces are packed before anything is received, like the reference (boundaries.f90:70-75)
   const Grid& g = s->A.g;
   const int lo = s->nbr[dir][0], hi = s->nbr[dir][1];
   if (lo < 0 && hi < 0) return GX_OK;
   if (!s->comm) return fail(GX_ECOMM, "block has neighbours but no communicator is attached (gx_comm_attach)");
+  if (dir == 2 && s->p2p && peer_array(s, lo >= 0 ? 0 : 1, A)) return exchange_z_p2p(s, A, nvar, nl);
   const Box sb_lo = face_box(g, dir, 0, nl, false), sb_hi = face_box(g, dir, 1, nl, false);
   const size_t cnt = box_cells(sb_lo) * nvar;
   if (cnt > s->halo_doubles[dir]) return fail(GX_ESTATE, "halo buffer too small");
@@ -592,6 +654,16 @@ int gx_destroy(gx_solver* s) {
   if (!s) return GX_OK;
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->p2p && s->comm && g_nccl.ok) {          // nobody may unmap or free while a neighbour can still push into these arrays
+    g_nccl.AllReduce(s->flags + FL_WORDS - 1, s->flags + FL_WORDS - 1, 1, ncclUint32, ncclSum, s->comm, s->stream);
+    cudaStreamSynchronize(s->stream);
+  }
+  for (int side = 0; side < 2; ++side) {
+    if (side == 1 && s->peer[1].U == s->peer[0].U) break;
+    void* ptrs[] = {s->peer[side].U, s->peer[side].UP, s->peer[side].E, s->peer[side].flags};
+    for (void* p : ptrs) if (p) cudaIpcCloseMemHandle(p);
+  }
+  if (s->flags) cudaFree(s->flags);
   if (s->comm && g_nccl.ok) g_nccl.CommDestroy(s->comm);
   double* ptrs[] = {s->U, s->UP, s->W, s->F, s->E, s->Temp, s->stage};
   for (double* p : ptrs) if (p) cudaFree(p);
@@ -852,6 +924,56 @@ int gx_comm_attach(gx_solver* s, const void* idp, int32_t nbytes, int32_t rank, 
   ncclUniqueId id; memcpy(&id, idp, sizeof id);
   NCCL_TRY(g_nccl.CommInitRank(&s->comm, nranks, id, rank));
   s->nranks = nranks;
+  // z slabs: map the neighbours' arrays (CUDA IPC) for the peer-memory halo push; any failure keeps the NCCL path
+  if (s->nb[0] == 1 && s->nb[1] == 1 && s->nb[2] > 1 && !getenv("GX_NO_P2P") && load_stream_memops()) {
+    struct Pack { cudaIpcMemHandle_t h[4]; int have_e; int pad[3]; };
+    Pack mine; memset(&mine, 0, sizeof mine);
+    bool ok = true;
+    if (!s->flags) { ok = cudaMalloc((void**)&s->flags, FL_WORDS * sizeof(uint32_t)) == cudaSuccess && cudaMemset(s->flags, 0, FL_WORDS * sizeof(uint32_t)) == cudaSuccess; }
+    ok = ok && cudaIpcGetMemHandle(&mine.h[0], s->U) == cudaSuccess && cudaIpcGetMemHandle(&mine.h[1], s->UP) == cudaSuccess &&
+         cudaIpcGetMemHandle(&mine.h[3], s->flags) == cudaSuccess;
+    if (ok && s->E) { ok = cudaIpcGetMemHandle(&mine.h[2], s->E) == cudaSuccess; mine.have_e = 1; }
+    // every rank must take the same branch below: agree on `ok` first (min over ranks)
+    int* d_ok = nullptr; Pack* d_pk = nullptr;               // d_pk[0] = mine, [1] = from lo, [2] = from hi
+    if (cudaMalloc((void**)&d_ok, sizeof(int)) != cudaSuccess || cudaMalloc((void**)&d_pk, 3 * sizeof(Pack)) != cudaSuccess) return fail(GX_ENOMEM, "peer link buffers");
+    int okv = ok ? 1 : 0;
+    CUDA_TRY(cudaMemcpy(d_ok, &okv, sizeof okv, cudaMemcpyHostToDevice));
+    NCCL_TRY(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, s->comm, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(&okv, d_ok, sizeof okv, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (okv) {
+      const int lo = s->nbr[2][0], hi = s->nbr[2][1];
+      CUDA_TRY(cudaMemcpy(d_pk, &mine, sizeof mine, cudaMemcpyHostToDevice));
+      NCCL_TRY(g_nccl.GroupStart());                          // same pairing order as the halo exchange
+      if (hi >= 0) NCCL_TRY(g_nccl.Send(d_pk, sizeof(Pack), ncclUint8, hi, s->comm, s->stream));
+      if (lo >= 0) NCCL_TRY(g_nccl.Recv(d_pk + 1, sizeof(Pack), ncclUint8, lo, s->comm, s->stream));
+      if (lo >= 0) NCCL_TRY(g_nccl.Send(d_pk, sizeof(Pack), ncclUint8, lo, s->comm, s->stream));
+      if (hi >= 0) NCCL_TRY(g_nccl.Recv(d_pk + 2, sizeof(Pack), ncclUint8, hi, s->comm, s->stream));
+      NCCL_TRY(g_nccl.GroupEnd());
+      Pack got[3];
+      CUDA_TRY(cudaMemcpyAsync(got, d_pk, sizeof got, cudaMemcpyDeviceToHost, s->stream));
+      CUDA_TRY(cudaStreamSynchronize(s->stream));
+      int opened = 1;
+      for (int side = 0; side < 2 && opened; ++side) {
+        const int nb = side == 0 ? lo : hi;
+        if (nb < 0) continue;
+        if (side == 1 && hi == lo) { s->peer[1] = s->peer[0]; continue; }       // two blocks, periodic: one neighbour on both sides
+        const Pack& pk = got[1 + side];
+        void* ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+        for (int q = 0; q < 4; ++q) {
+          if (q == 2 && !pk.have_e) continue;
+          if (cudaIpcOpenMemHandle(&ptr[q], pk.h[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened = 0; break; }
+        }
+        s->peer[side].U = (double*)ptr[0]; s->peer[side].UP = (double*)ptr[1]; s->peer[side].E = (double*)ptr[2]; s->peer[side].flags = (uint32_t*)ptr[3];
+      }
+      CUDA_TRY(cudaMemcpy(d_ok, &opened, sizeof opened, cudaMemcpyHostToDevice));
+      NCCL_TRY(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, s->comm, s->stream));
+      CUDA_TRY(cudaMemcpyAsync(&opened, d_ok, sizeof opened, cudaMemcpyDeviceToHost, s->stream));
+      CUDA_TRY(cudaStreamSynchronize(s->stream));
+      s->p2p = opened != 0;
+    }
+    cudaFree(d_ok); cudaFree(d_pk);
+  }
   return GX_OK;
 }
 
