@@ -67,6 +67,9 @@ struct gx_solver {
   const gx::KernelTable* K = nullptr;
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t cstream = nullptr;                             // halo push stream (overlaps the interior launches)
+  cudaEvent_t ev_bnd = nullptr, ev_comm = nullptr;
+  bool overlap = false;                                       // z slabs + peer push: boundary-first launches, exchange on cstream
   double *U = nullptr, *UP = nullptr, *W = nullptr, *F = nullptr, *E = nullptr, *Temp = nullptr;
   double* stage = nullptr; size_t stage_doubles = 0;         // AoS staging for layout conversion
   double* halo_send[6] = {0, 0, 0, 0, 0, 0};                  // packed faces (multi-GPU)
@@ -119,6 +122,7 @@ struct LaunchScope {
 static void collect_timed(gx_solver* s) {
   if (s->timed.empty()) return;
   cudaStreamSynchronize(s->stream);
+  if (s->cstream) cudaStreamSynchronize(s->cstream);
   for (auto& t : s->timed) {
     float ms = 0; cudaEventElapsedTime(&ms, t.a, t.b);
     s->cls_ms[t.cls] += ms; s->cls_n[t.cls] += 1;
@@ -402,14 +406,13 @@ static bool load_stream_memops() {
 static double* peer_array(const gx_solver* s, int side, const double* A) {
   return A == s->U ? s->peer[side].U : A == s->UP ? s->peer[side].UP : A == s->E ? s->peer[side].E : nullptr;
 }
-static int exchange_z_p2p(gx_solver* s, double* A, int nvar, int nl) {
+static int exchange_z_p2p(gx_solver* s, double* A, int nvar, int nl, cudaStream_t st) {
   const Grid& g = s->A.g;
   const int lo = s->nbr[2][0], hi = s->nbr[2][1];
   const long long plane = (long long)g.px * g.py;
   const size_t pitch = (size_t)g.vs * sizeof(double), width = (size_t)nl * plane * sizeof(double);
   const unsigned seq = ++s->xseq;
   const unsigned GEQ = 0;                               // CU_STREAM_WAIT_VALUE_GEQ (the words only ever grow)
-  cudaStream_t st = s->stream;
   auto W = [&](uint32_t* base, int word) { return g_write32(st, (unsigned long long)(uintptr_t)(base + word), seq, 0); };
   auto T = [&](int word) { return g_wait32(st, (unsigned long long)(uintptr_t)(s->flags + word), seq, GEQ); };
   int e = 0;
@@ -433,13 +436,14 @@ static int exchange_z_p2p(gx_solver* s, double* A, int nvar, int nl) {
   return GX_OK;
 }
 
-static int exchange_dir(gx_solver* s, double* A, int nvar, int nl, int dir) {
+static int exchange_dir(gx_solver* s, double* A, int nvar, int nl, int dir, cudaStream_t st = nullptr) {
+  if (!st) st = s->stream;
   // all faces are packed before anything is received, like the reference (boundaries.f90:70-75)
   const Grid& g = s->A.g;
   const int lo = s->nbr[dir][0], hi = s->nbr[dir][1];
   if (lo < 0 && hi < 0) return GX_OK;
   if (!s->comm) return fail(GX_ECOMM, "block has neighbours but no communicator is attached (gx_comm_attach)");
-  if (dir == 2 && s->p2p && peer_array(s, lo >= 0 ? 0 : 1, A)) return exchange_z_p2p(s, A, nvar, nl);
+  if (dir == 2 && s->p2p && peer_array(s, lo >= 0 ? 0 : 1, A)) return exchange_z_p2p(s, A, nvar, nl, st);
   const Box sb_lo = face_box(g, dir, 0, nl, false), sb_hi = face_box(g, dir, 1, nl, false);
   const size_t cnt = box_cells(sb_lo) * nvar;
   if (cnt > s->halo_doubles[dir]) return fail(GX_ESTATE, "halo buffer too small");
@@ -472,14 +476,16 @@ static void launch_bc_face(gx_solver* s, double* A, int nvar, int dir, int side,
 // kind 0: conserved/primitive array (closed wall flips normal momentum, boundaries.f90:146-199, 361-438)
 // kind 1: electric field (closed wall flips e(1) on x walls, e(2) on y walls, nothing on z walls,
 //         flux_cd_module.f90:143-192)
-static int apply_boundaries(gx_solver* s, double* A, int nvar, int nl, int kind, bool skip_wrapped = false) {
+// `st`: only the overlapped step passes the halo stream, and only when every direction but z is wrapped in the loaders
+// and z goes through the peer push (no kernels of this function then run besides the physical fills at the z ends)
+static int apply_boundaries(gx_solver* s, double* A, int nvar, int nl, int kind, bool skip_wrapped = false, cudaStream_t st = nullptr) {
   for (int dir = 0; dir < 3; ++dir) {
     if (s->nb[dir] == 1 && s->periodic[dir]) {            // neighbour is the block itself
       if (skip_wrapped && s->A.wrap[dir]) continue;       // the fused kernels wrap their reads instead
       launch_bc_face(s, A, nvar, dir, 0, 0, nl, -1);
       launch_bc_face(s, A, nvar, dir, 1, 0, nl, -1);
     } else {
-      int rc = exchange_dir(s, A, nvar, nl, dir);
+      int rc = exchange_dir(s, A, nvar, nl, dir, st);
       if (rc) return rc;
     }
   }
@@ -579,6 +585,7 @@ int gx_create(const gx_config* c, gx_solver** out) {
   s->A.solver = c->riemann_solver; s->A.limiter = c->slope_limiter;
   s->A.flux_cd = c->enable_flux_cd; s->A.eight_wave = c->eight_wave; s->A.user_src = c->user_source_terms;
   s->A.grav.n = 0;
+  s->A.kbeg = 1; s->A.klast = nz;
   s->K = c->strict_fp ? gx::kernels_strict() : gx::kernels_fast();
 
   s->nb[0] = c->nbx; s->nb[1] = c->nby; s->nb[2] = c->nbz;
@@ -654,6 +661,7 @@ int gx_destroy(gx_solver* s) {
   if (!s) return GX_OK;
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->cstream) cudaStreamSynchronize(s->cstream);
   if (s->p2p && s->comm && g_nccl.ok) {          // nobody may unmap or free while a neighbour can still push into these arrays
     g_nccl.AllReduce(s->flags + FL_WORDS - 1, s->flags + FL_WORDS - 1, 1, ncclUint32, ncclSum, s->comm, s->stream);
     cudaStreamSynchronize(s->stream);
@@ -673,6 +681,9 @@ int gx_destroy(gx_solver* s) {
   for (auto e : s->evpool) cudaEventDestroy(e);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->ev_bnd) cudaEventDestroy(s->ev_bnd);
+  if (s->ev_comm) cudaEventDestroy(s->ev_comm);
+  if (s->cstream) cudaStreamDestroy(s->cstream);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
   return GX_OK;
@@ -776,7 +787,54 @@ static int tstep_enqueue_fused(gx_solver* s, double dt_cfl) {
   return GX_OK;
 }
 
+// tstep, fused kernels, z slabs with the peer-memory push: every producer of exchanged data (the stage kernels for
+// E, k_bupdate for the B part of up / u) is launched boundary planes first; the push of those planes then runs on
+// the halo stream — copy engines and stream memory operations only, no SM — while the interior launch runs on the
+// solver's stream ("overlapped with interior-cell updates").  Exchange order and contents are the
+// reference's (E, up 2 layers, E, u 1 layer); results are bitwise those of the serialized path.
+static int tstep_enqueue_fused_overlap(gx_solver* s, double dt_cfl) {
+  const gx::KernelTable* K = s->K;
+  const int neq = s->A.g.neq, nz = s->A.g.nz;
+  const double dtm = dt_cfl / 2.;
+  const int kb = 4;                                   // boundary thickness of the stage launches (>= 2: up sends 2 layers)
+  StepArgs lo = s->A, hi = s->A, mid = s->A;
+  lo.kbeg = 1; lo.klast = kb; hi.kbeg = nz - kb + 1; hi.klast = nz; mid.kbeg = kb + 1; mid.klast = nz - kb;
+  StepArgs blo = s->A, bhi = s->A, bmid = s->A;       // B update: exactly the layers that travel
+  blo.kbeg = 1; blo.klast = 2; bhi.kbeg = nz - 1; bhi.klast = nz; bmid.kbeg = 3; bmid.klast = nz - 2;
+  int rc;
+  auto fork = [&]() { cudaEventRecord(s->ev_bnd, s->stream); cudaStreamWaitEvent(s->cstream, s->ev_bnd, 0); };
+  auto join = [&]() { cudaEventRecord(s->ev_comm, s->cstream); cudaStreamWaitEvent(s->stream, s->ev_comm, 0); };
+  auto stage = [&](int cls, int order, double dt, const double* S, const double* Ub, double* dst) -> int {
+    for (const StepArgs* a : {&lo, &hi}) {
+      LaunchScope ls(s, cls);
+      int r = K->stage(*a, order, dt, S, Ub, dst, s->E, s->kz, nullptr, 0, &s->dscal->err, s->stream); if (r) return r;
+    }
+    fork();
+    int r = apply_boundaries(s, s->E, 3, 1, 1, true, s->cstream); if (r) return r;      // boundaryI_ef
+    { LaunchScope ls(s, cls); r = K->stage(mid, order, dt, S, Ub, dst, s->E, s->kz, nullptr, 0, &s->dscal->err, s->stream); if (r) return r; }
+    join();
+    return GX_OK;
+  };
+  auto bupdate = [&](double dt, const double* Ub, double* dst, int nl, unsigned long long* dtmin, int want_cfl) -> int {
+    for (const StepArgs* a : {&blo, &bhi}) { LaunchScope ls(s, gx::KC_BUPDATE); K->bupdate(*a, dt, Ub, s->E, dst, dtmin, want_cfl, s->stream); }
+    fork();
+    int r = apply_boundaries(s, dst, neq, nl, 0, true, s->cstream); if (r) return r;    // boundaryII (nl = 2) / boundaryI (nl = 1)
+    { LaunchScope ls(s, gx::KC_BUPDATE); K->bupdate(bmid, dt, Ub, s->E, dst, dtmin, want_cfl, s->stream); }
+    join();
+    return GX_OK;
+  };
+  rc = stage(gx::KC_STAGE1, 1, dtm, s->U, s->U, s->UP); if (rc) return fail(rc, "stage-1 launch");
+  rc = bupdate(dtm, s->U, s->UP, 2, nullptr, 0); if (rc) return rc;
+  rc = reset_dtmin(s); if (rc) return rc;
+  rc = stage(gx::KC_STAGE2, 2, dt_cfl, s->UP, s->U, s->U); if (rc) return fail(rc, "stage-2 launch");
+  rc = bupdate(dt_cfl, s->U, s->U, 1, &s->dscal->dtmin_bits, 1); if (rc) return rc;
+  s->ghosts_stale = true;
+  CUDA_TRY(cudaGetLastError());
+  return GX_OK;
+}
+
 static int tstep_enqueue(gx_solver* s, double dt_cfl) {
+  if (s->fused && s->overlap) return tstep_enqueue_fused_overlap(s, dt_cfl);
   if (s->fused) return tstep_enqueue_fused(s, dt_cfl);
   const gx::KernelTable* K = s->K;
   const StepArgs& A = s->A;
@@ -971,6 +1029,15 @@ int gx_comm_attach(gx_solver* s, const void* idp, int32_t nbytes, int32_t rank, 
       CUDA_TRY(cudaMemcpyAsync(&opened, d_ok, sizeof opened, cudaMemcpyDeviceToHost, s->stream));
       CUDA_TRY(cudaStreamSynchronize(s->stream));
       s->p2p = opened != 0;
+      // periodic z (no physical fills at the slab ends), x and y wrapped in the loaders, flux-CD: overlap the push
+      s->overlap = s->p2p && s->fused && s->A.flux_cd && s->periodic[2] && s->A.wrap[0] && s->A.wrap[1] && s->A.g.nz >= 16 &&
+                   !s->cfg.bc_user && !getenv("GX_NO_OVERLAP");
+      if (s->overlap && !s->cstream) {
+        int lo_p = 0, hi_p = 0; cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+        CUDA_TRY(cudaStreamCreateWithPriority(&s->cstream, cudaStreamNonBlocking, hi_p));
+        CUDA_TRY(cudaEventCreateWithFlags(&s->ev_bnd, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&s->ev_comm, cudaEventDisableTiming));
+      }
     }
     cudaFree(d_ok); cudaFree(d_pk);
   }

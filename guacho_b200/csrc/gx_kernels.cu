@@ -221,7 +221,7 @@ template <bool CFL>
 __global__ void __launch_bounds__(256) k_bupdate(const StepArgs A, double dt, const double* Ub, const double* __restrict__ E,
                                                  double* dst, unsigned long long* dtmin_bits) {
   const Grid& g = A.g;
-  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) + 1, j = (int)blockIdx.y + 1, k = (int)blockIdx.z + 1;
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) + 1, j = (int)blockIdx.y + 1, k = (int)blockIdx.z + A.kbeg;
   double dtp = 1.e30;
   if (i <= g.nx) {
     const long long c = g.idx(i, j, k), sy = g.px, sz = (long long)g.px * g.py, vs = g.vs;
@@ -330,7 +330,7 @@ static int l_stage(const StepArgs& A, int order, double dt, const double* S, con
 
 static void l_bupdate(const StepArgs& A, double dt, const double* Ub, const double* E, double* dst, unsigned long long* dtmin_bits, int want_cfl, cudaStream_t s) {
   const Grid& g = A.g;
-  dim3 grid = grid_for(g.nx, g.ny, g.nz, 256);
+  dim3 grid = grid_for(g.nx, g.ny, A.klast - A.kbeg + 1, 256);
   if (want_cfl) k_bupdate<true><<<grid, 256, 0, s>>>(A, dt, Ub, E, dst, dtmin_bits);
   else k_bupdate<false><<<grid, 256, 0, s>>>(A, dt, Ub, E, dst, dtmin_bits);
 }

@@ -36,6 +36,8 @@ struct StepArgs {
   int wrap[3];             // direction is periodic with the block as its own neighbour: the fused
                            // kernels read the wrapped cell instead of a ghost cell (ghosts are
                            // then only materialised when the host asks for the arrays)
+  int kbeg, klast;         // planes (Fortran k) the fused stage / B-update launch covers; 1..nz unless the step is split into
+                           // boundary-first and interior launches to overlap the halo exchange (multi-GPU)
   gxp::Phys phys;
   int solver, limiter;
   int flux_cd, eight_wave, user_src;

@@ -167,8 +167,8 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
 
   const Grid& g = A.g;
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-  const int i0 = 1 + (int)blockIdx.x * TX, j0 = 1 + (int)blockIdx.y * TY, k0 = 1 + (int)blockIdx.z * kz;
-  const int kend = min(k0 + kz - 1, g.nz);
+  const int i0 = 1 + (int)blockIdx.x * TX, j0 = 1 + (int)blockIdx.y * TY, k0 = A.kbeg + (int)blockIdx.z * kz;
+  const int kend = min(k0 + kz - 1, A.klast);
   const long long vs = g.vs;
 
   // ---- plane staging: conserved -> shared (cp.async), converted in place to primitives ----
@@ -350,7 +350,7 @@ static int launch_one(const StepArgs& A, double dt, const double* S, const doubl
   auto kern = k_stage<SOLVER, LIM, ORDER, FLUXCD>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM) != cudaSuccess) return GX_ECUDA;
   const Grid& g = A.g;
-  dim3 grid((g.nx + G::TX - 1) / G::TX, (g.ny + G::TY - 1) / G::TY, (g.nz + kz - 1) / kz);
+  dim3 grid((g.nx + G::TX - 1) / G::TX, (g.ny + G::TY - 1) / G::TY, (A.klast - A.kbeg + 1 + kz - 1) / kz);
   kern<<<grid, G::NT, G::SMEM, st>>>(A, dt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag);
   return GX_OK;
 }
