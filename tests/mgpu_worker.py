@@ -3,7 +3,7 @@
 Every rank advances its block of a decomposed domain through the C ABI (NCCL halo exchange and
 CFL all-reduce inside libguacho_gx.so); rank 0 also advances the same problem as ONE block and
 checks that the gathered interiors are bitwise equal (G-GPU == 1-GPU).
-usage: mgpu_worker.py NBX NBY NBZ NX NY NZ NSTEPS PROBLEM [strict]
+usage: mgpu_worker.py NBX NBY NBZ NX NY NZ NSTEPS PROBLEM [strict] [outflowz]
 """
 import os
 import sys
@@ -27,11 +27,14 @@ def main():
 
     nbx, nby, nbz, nx, ny, nz, nsteps = (int(a) for a in sys.argv[1:8])
     problem = sys.argv[8]
-    strict = len(sys.argv) > 9 and sys.argv[9] == "strict"
+    strict = "strict" in sys.argv[9:]
+    outflowz = "outflowz" in sys.argv[9:]           # physical (mirror) boundaries at the ends of the z decomposition
     rank, local_rank, world = init_process_group("nccl")
     assert world == nbx * nby * nbz
     torch.cuda.set_device(local_rank)
-    p = Params(nxtot=nx, nytot=ny, nztot=nz, zmax=1.0, strict_fp=strict)
+    from guacho_b200.config import BC_OUTFLOW
+    kw = dict(bc_out=BC_OUTFLOW, bc_in=BC_OUTFLOW) if outflowz else {}
+    p = Params(nxtot=nx, nytot=ny, nztot=nz, zmax=1.0, strict_fp=strict, **kw)
     nb = (nbx, nby, nbz)
     blk = make_rank_block(p, rank, world, local_rank, nb=nb)
     coords = coords_of(rank, nb)

@@ -15,12 +15,13 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-def _run(nb, grid, nsteps, problem, strict=False, port=29541):
+def _run(nb, grid, nsteps, problem, strict=False, port=29541, extra=()):
     world = nb[0] * nb[1] * nb[2]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py"), *map(str, nb), *map(str, grid), str(nsteps), problem]
     if strict:
         cmd.append("strict")
+    cmd.extend(extra)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "OK" in r.stdout
@@ -37,3 +38,19 @@ def test_four_gpu_pencils_bitwise():
     if _ngpu() < 4:
         pytest.skip("needs 4 GPUs")
     _run((1, 2, 2), (64, 48, 40), 3, "random", port=29543)
+
+
+def test_two_gpu_z_slabs_with_physical_ends_bitwise():
+    """Outflow (mirror) boundaries at the two ends of the z decomposition: each rank has one real neighbour and one
+    physical face; the peer-memory push runs serialized (no overlap) next to the ghost-fill kernels."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run((1, 1, 2), (64, 48, 40), 3, "blast", port=29545, extra=("outflowz",))
+
+
+def test_four_gpu_z_slabs_bitwise():
+    """Four z slabs, periodic: distinct low/high neighbours for every rank — the decomposition bench.py uses for
+    weak scaling (peer-memory push overlapped with the interior launches)."""
+    if _ngpu() < 4:
+        pytest.skip("needs 4 GPUs")
+    _run((1, 1, 4), (64, 48, 80), 3, "random", port=29546)
