@@ -274,9 +274,11 @@ def main():
     tot_prof = sum(v[0] for v in ktimes.values())
     fused = ktimes["stage2"][1] > 0
     if fused:
-        # dominant kernel: the fused 2nd-order stage (k_stage<HLLD,minmod,2,fluxcd>); its algorithmic
-        # traffic is: read U* (neq) and U^n (neq), write U^{n+1} (neq) = 3*neq doubles per zone
-        dom_name, dom_key, dom_bytes_zone = "k_stage<HLLD,minmod,ORDER=2,fluxCD> (fused prim+3 sweeps+E+update)", "stage2", 3 * 8 * pb.neq
+        # dominant kernel: the fused 2nd-order stage k_stage<HLLD,minmod,2,fluxcd>.  Its algorithmic traffic per zone:
+        # read U* (neq) and the non-B part of U^n (5), write the non-B part of U^{n+1} (5) and E (3) = 21 doubles with
+        # flux-CD (the B part of the stage belongs to k_bupdate); 3*neq doubles without flux-CD.
+        dom_doubles = (pb.neq + 5 + 5 + 3) if pb.enable_flux_cd else 3 * pb.neq
+        dom_name, dom_key, dom_bytes_zone = "k_stage<HLLD,minmod,ORDER=2,fluxCD> (fused prim+3 sweeps+E+update)", "stage2", 8 * dom_doubles
     else:
         dom_name, dom_key, dom_bytes_zone = "k_flux<HLLD,minmod> (3 launches per stage, unfused path)", "flux", 2 * 8 * pb.neq * 3
     dom_ms, dom_n = ktimes[dom_key]
@@ -295,7 +297,7 @@ def main():
         "bound": "hbm", "achieved": dom_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": (dom_gbs / peak_gbs if dom_gbs else None), "traffic": traffic,
         "peak_source": peak_src, "kernel": dom_name, "avg_launch_ms": dom_avg_ms,
         "algorithmic_bytes_per_zone": dom_bytes_zone,
-        "definition": "algorithmic bytes of the dominant kernel (3*neq doubles per zone) x zones per GPU / its average launch time (CUDA events on the solver's stream)",
+        "definition": "algorithmic bytes of the dominant kernel (read U* 8 + U^n 5, write U^{n+1} 5 + E 3 = 21 doubles per zone with flux-CD) x zones per GPU / its average launch time (CUDA events on the solver's stream)",
         "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak_gbs, "algorithmic_bytes_per_zone": BYTES_PER_ZONE,
                        "definition": "320 B per zone-update (5*neq doubles) x zones per GPU / whole-step device time"},
         "fp64_note": "the kernel is FP64-pipe/latency bound, not HBM bound: see profiles/ (sm__inst_executed_pipe_fp64 ~43%, dram ~15%) and DESIGN.md",
