@@ -106,11 +106,18 @@ class ClockSampler:
         return out
 
 
-def workload(n: int, world: int, strong: bool = False) -> Params:
+SOLVERS = {"hll": (1, False), "hllc": (2, False), "hlle": (3, True), "hlld": (4, True)}   # name -> (SOLVER_*, MHD)
+
+
+def workload(n: int, world: int, strong: bool = False, solver: str = "hlld") -> Params:
     if strong:   # strong scaling: n^3 in total, z-slabs of n/world planes (BASELINE configs[2] "512^3 ... strong")
-        return ot_3d(n)
-    # weak scaling (default): the same n^3 block per GPU, stacked along z
-    return ot_3d(n, nztot=n * world, zmax=1.0 * world)
+        p = ot_3d(n)
+    else:        # weak scaling (default): the same n^3 block per GPU, stacked along z
+        p = ot_3d(n, nztot=n * world, zmax=1.0 * world)
+    sv, mhd = SOLVERS[solver]
+    if solver != "hlld":   # BASELINE configs[4], the solver sweep: HLL/HLLC are hydro (neq = 5), HLLE is MHD + flux-CD
+        p = p.replace(riemann_solver=sv, mhd=mhd, enable_flux_cd=mhd)
+    return p
 
 
 def cpu_reference(p_block: Params, steps: int, warmup: int, threads: int):
@@ -162,6 +169,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strict", action="store_true", help="use the -fmad=false bit-comparison kernels")
+    ap.add_argument("--solver", default="hlld", choices=sorted(SOLVERS), help="Riemann solver (BASELINE configs[4] sweep); the headline metric is hlld")
     ap.add_argument("--strong", action="store_true", help="strong scaling: --n is the TOTAL grid side, split into z-slabs over the GPUs")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -182,7 +190,7 @@ def main():
 
     if args.strong and args.n % world:
         raise SystemExit(f"--strong: {args.n} planes do not split over {world} GPUs")
-    p = workload(args.n, world, args.strong).replace(strict_fp=args.strict)
+    p = workload(args.n, world, args.strong, args.solver).replace(strict_fp=args.strict)
     nb = (1, 1, world)
     blk = make_rank_block(p, rank, world, local_rank, nb=nb)
     pb = blk.p
@@ -278,7 +286,7 @@ def main():
         # read U* (neq) and the non-B part of U^n (5), write the non-B part of U^{n+1} (5) and E (3) = 21 doubles with
         # flux-CD (the B part of the stage belongs to k_bupdate); 3*neq doubles without flux-CD.
         dom_doubles = (pb.neq + 5 + 5 + 3) if pb.enable_flux_cd else 3 * pb.neq
-        dom_name, dom_key, dom_bytes_zone = "k_stage<HLLD,minmod,ORDER=2,fluxCD> (fused prim+3 sweeps+E+update)", "stage2", 8 * dom_doubles
+        dom_name, dom_key, dom_bytes_zone = f"k_stage<{args.solver.upper()},minmod,ORDER=2{',fluxCD' if pb.enable_flux_cd else ''}> (fused prim+3 sweeps+E+update)", "stage2", 8 * dom_doubles
     else:
         dom_name, dom_key, dom_bytes_zone = "k_flux<HLLD,minmod> (3 launches per stage, unfused path)", "flux", 2 * 8 * pb.neq * 3
     dom_ms, dom_n = ktimes[dom_key]
@@ -288,18 +296,19 @@ def main():
     try:       # DRAM bytes of that kernel per launch from the committed ncu --set full capture (same workload only)
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
             tj = json.load(f)
-        if fused and tj.get("zones") == zones_rank:
+        if fused and tj.get("zones") == zones_rank and args.solver == "hlld":
             traffic = tj["stage2_dram_bytes_per_launch"]
     except Exception:
         pass
-    step_gbs = BYTES_PER_ZONE * zones_rank / (step_ms * 1e-3) / 1e9
+    bytes_zone = 40.0 * pb.neq                        # 5*neq doubles: 320 B (MHD), 200 B (hydro)
+    step_gbs = bytes_zone * zones_rank / (step_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "achieved": dom_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": (dom_gbs / peak_gbs if dom_gbs else None), "traffic": traffic,
         "peak_source": peak_src, "kernel": dom_name, "avg_launch_ms": dom_avg_ms,
         "algorithmic_bytes_per_zone": dom_bytes_zone,
         "definition": "algorithmic bytes of the dominant kernel (read U* 8 + U^n 5, write U^{n+1} 5 + E 3 = 21 doubles per zone with flux-CD) x zones per GPU / its average launch time (CUDA events on the solver's stream)",
-        "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak_gbs, "algorithmic_bytes_per_zone": BYTES_PER_ZONE,
-                       "definition": "320 B per zone-update (5*neq doubles) x zones per GPU / whole-step device time"},
+        "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak_gbs, "algorithmic_bytes_per_zone": bytes_zone,
+                       "definition": "40*neq B per zone-update (5*neq doubles: 320 B MHD, 200 B hydro) x zones per GPU / whole-step device time"},
         "fp64_note": "the kernel is FP64-pipe/latency bound, not HBM bound: see profiles/ (sm__inst_executed_pipe_fp64 ~43%, dram ~15%) and DESIGN.md",
         "kernel_share": {k: (v[0] / tot_prof if tot_prof > 0 else None) for k, v in ktimes.items() if v[1]},
         "kernel_ms_per_step": {k: v[0] / nprof for k, v in ktimes.items() if v[1]},
@@ -311,12 +320,13 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC if args.solver == "hlld" else f"{'MHD' if pb.mhd else 'hydro'} zone-updates/s ({args.solver.upper()}{' + flux-CD' if pb.enable_flux_cd else ''}, FP64)",
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": (f"3-D Orszag-Tang {args.n}^3 in total (BASELINE configs[2], strong scaling)" if args.strong else f"3-D Orszag-Tang {args.n}^3 per GPU (BASELINE configs[1])") + ", HLLD + flux-CD, minmod, periodic, cfl 0.2",
+        "config": {"workload": (f"3-D Orszag-Tang {args.n}^3 in total (BASELINE configs[2], strong scaling)" if args.strong else f"3-D Orszag-Tang {args.n}^3 per GPU (BASELINE configs[1])") + ", " + (f"{args.solver.upper()}" + (" + flux-CD" if pb.enable_flux_cd else "")) + ", minmod, periodic, cfl 0.2",
                    "grid_total": [pb.nxtot, pb.nytot, pb.nztot], "blocks": list(nb), "neq": pb.neq,
                    "kernels": "strict (-fmad=false)" if args.strict else "fast (-fmad=true)",
-                   "l2": "working set (u, up, E: 2.7 GB per GPU at 256^3) exceeds the 126 MB L2; no flush needed",
+                   "l2": f"working set (u, up, E: {(2 * pb.neq + 3) * 8 * (pb.nx + 32) * (pb.ny + 4) * (pb.nz + 4) / 1e9:.1f} GB per GPU) exceeds the 126 MB L2; no flush needed",
                    "halo_bytes_per_step_per_gpu": halo_bytes_per_step(pb)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes + 16,

@@ -297,7 +297,7 @@ __device__ __forceinline__ int riemann_hll(const Phys& P, const double (&wl)[8],
 }
 
 // ---- HLLC: src/hllc.f90:44-140 (hydro) ----
-__device__ __forceinline__ int riemann_hllc(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
+__device__ __forceinline__ int riemann_hllc_ref(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
   double csl = csound(P, wl[4], wl[0]);
   double csr = csound(P, wr[4], wr[0]);
   double sr = gx_max(wl[1] + csl, wr[1] + csr);
@@ -343,6 +343,44 @@ __device__ __forceinline__ int riemann_hllc(const Phys& P, const double (&wl)[8]
   }
   return 1;   // NaN: the reference prints 'Error in hllc' and stops (hllc.f90:135-138)
 }
+
+#if defined(GX_FLAVOUR_FAST)
+// Production HLLC: the same expressions as riemann_hllc_ref / src/hllc.f90:44-140 in one basic block — the side K
+// that supplies the star state (L for S* >= 0, R otherwise) is chosen by selects, the four divisions become
+// Newton-refined reciprocals (1/rho_K shared), and the two supersonic cases are a rare override at the end.
+__device__ __forceinline__ int riemann_hllc(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
+  const double irl = fast_rcp(wl[0]), irr = fast_rcp(wr[0]);
+  const double csl = gx_sqrt(P.gamma * wl[4] * irl), csr = gx_sqrt(P.gamma * wr[4] * irr);
+  const double sr = gx_max(wl[1] + csl, wr[1] + csr);
+  const double sl = gx_min(wl[1] - csl, wr[1] - csr);
+  I.ul = wl[1]; I.ur = wr[1]; I.sl = sl; I.sr = sr;
+  const double slmul = sl - wl[1], srmur = sr - wr[1];
+  const double mL = wl[0] * slmul, mR = wr[0] * srmur;
+  const double sst = (mR * wr[1] - mL * wl[1] - wr[4] + wl[4]) * fast_rcp(mR - mL);          // hllc.f90:76-77
+  const bool left = sst >= 0.;
+  const int err = (!left && !(sst <= 0.)) ? 1 : 0;                                               // NaN: 'Error in hllc' + stop (:135-138)
+  const double q0 = left ? wl[0] : wr[0], q1 = left ? wl[1] : wr[1], q2 = left ? wl[2] : wr[2], q3 = left ? wl[3] : wr[3], q4 = left ? wl[4] : wr[4];
+  const double sK = left ? sl : sr, sKmu = left ? slmul : srmur, mK = left ? mL : mR, irK = left ? irl : irr;
+  const double rhost = mK * fast_rcp(sK - sst);                                                  // :80, :108
+  const double ek = 0.5 * q0 * (q1 * q1 + q2 * q2 + q3 * q3) + P.cv * q4;
+  const double uk4 = rhost * (ek * irK + (sst - q1) * (sst + q4 * fast_rcp(mK)));                // :86-87
+  const double m1 = q0 * q1;                                                                     // prim2f / prim2u of side K
+  ff[0] = m1 + sK * (rhost - q0);
+  ff[1] = (m1 * q1 + q4) + sK * (rhost * sst - m1);
+  ff[2] = m1 * q2 + sK * (rhost * q2 - q0 * q2);
+  ff[3] = m1 * q3 + sK * (rhost * q3 - q0 * q3);
+  ff[4] = q1 * (ek + q4) + sK * (uk4 - ek);
+  I.mode = left ? PAS_HLLC_L : PAS_HLLC_R; I.a = rhost; I.b = q0;
+  (void)sKmu;
+  if (sl > 0) { prim2f<false>(P, wl, ff); I.mode = PAS_UPL; return 0; }
+  if (sr < 0) { prim2f<false>(P, wr, ff); I.mode = PAS_UPR; return 0; }
+  return err;
+}
+#else
+__device__ __forceinline__ int riemann_hllc(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
+  return riemann_hllc_ref(P, wl, wr, ff, I);
+}
+#endif
 
 // ---- HLLD (Miyoshi & Kusano 2005 five-wave): src/hlld.f90:48-319 ----
 // One-sided star state (used for both sides with the roles of L/R exchanged).

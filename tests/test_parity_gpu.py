@@ -48,10 +48,11 @@ def test_ot_shipped_grid_one_step(strict):
     assert rel_err_per_var(wg, wo).max() <= TOL
 
 
+@pytest.mark.parametrize("strict", [True, False])
 @pytest.mark.parametrize("solver,mhd,cd", [(SOLVER_HLLD, True, True), (SOLVER_HLLD, True, False), (SOLVER_HLLE, True, True),
                                             (SOLVER_HLL, False, False), (SOLVER_HLLC, False, False)])
-def test_solvers_random_field_3d(solver, mhd, cd):
-    p = Params(nxtot=32, nytot=24, nztot=20, zmax=1.0, mhd=mhd, riemann_solver=solver, enable_flux_cd=cd, strict_fp=True)
+def test_solvers_random_field_3d(solver, mhd, cd, strict):
+    p = Params(nxtot=32, nytot=24, nztot=20, zmax=1.0, mhd=mhd, riemann_solver=solver, enable_flux_cd=cd, strict_fp=strict)
     ug, uo, wg, wo = run_pair(p, "random", nsteps=3)
     err = rel_err_per_var(ug, uo)
     assert err.max() <= TOL, err
