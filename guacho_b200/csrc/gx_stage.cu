@@ -187,12 +187,22 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
     return h - (H * CX + 2 * H * TY) + (H + TY) * CX;                           // rows above the tile
   };
   auto slot_off = [&](int p) { return ((p - (k0 - H)) % NSLOT) * G::PLANE; };
-  auto stage_cell = [&](double* sl, int c, int kk) {
+  // Every thread stages (and later converts) at most two cells of a plane: its own centre cell and one cell of
+  // the halo frame.  Their plane-local indices and their (i, j) offsets inside a global plane — clamped to the
+  // array, wrapped where the block is its own periodic neighbour — are fixed for the whole march: compute them once.
+  static_assert(HC <= NT, "one halo cell per thread");
+  const bool has_halo = tid < HC;
+  const int hcell = halo_cell(has_halo ? tid : 0);
+  auto ij_off = [&](int c) {
     const int rr = c / CX, cc = c - rr * CX;
     int i = min(i0 - H + cc, g.nx + 2), j = min(j0 - H + rr, g.ny + 2);
     if (A.wrap[0]) i = i < 1 ? i + g.nx : (i > g.nx ? i - g.nx : i);
     if (A.wrap[1]) j = j < 1 ? j + g.ny : (j > g.ny ? j - g.ny : j);
-    const double* src = S + g.idx(i, j, kk);
+    return (j + 1) * g.px + (i + g.xo);
+  };
+  const int own_off = ij_off(cidx), halo_off = ij_off(hcell);
+  const long long gplane = (long long)g.px * g.py;
+  auto stage_cell = [&](double* sl, int c, const double* src) {
 #pragma unroll
     for (int q = 0; q < NQ; ++q) cp_async8(sl + q * PC + c, src + q * vs);
   };
@@ -200,8 +210,9 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
     double* sl = ring + slot_off(p);
     int kk = min(p, g.nz + 2);
     if (A.wrap[2]) kk = kk < 1 ? kk + g.nz : (kk > g.nz ? kk - g.nz : kk);
-    if (main_warp) stage_cell(sl, cidx, kk);
-    for (int h = tid; h < HC; h += NT) stage_cell(sl, halo_cell(h), kk);
+    const double* pl = S + (long long)(kk + 1) * gplane;
+    if (main_warp) stage_cell(sl, cidx, pl + own_off);
+    if (has_halo) stage_cell(sl, hcell, pl + halo_off);
     cp_async_commit();
   };
   auto convert_cell = [&](double* sl, int c) {
@@ -215,7 +226,7 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
   auto convert = [&](int p) {      // each thread converts exactly the cells it staged itself
     double* sl = ring + slot_off(p);
     if (main_warp) convert_cell(sl, cidx);
-    for (int h = tid; h < HC; h += NT) convert_cell(sl, halo_cell(h));
+    if (has_halo) convert_cell(sl, hcell);
   };
 
   // Barriers of the plane loop (all NT threads arrive once per plane on each):
