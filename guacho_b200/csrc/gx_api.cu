@@ -604,9 +604,9 @@ int gx_create(const gx_config* c, gx_solver** out) {
 #define ALLOC(p, n) do { cudaError_t e_ = cudaMalloc((void**)&(p), (n)); if (e_ != cudaSuccess) { std::string m = cudaGetErrorString(e_); gx_destroy(s); return fail(GX_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", (size_t)(n), m.c_str()); } cudaMemsetAsync((p), 0, (n), 0); } while (0)
   cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   const size_t var_bytes = (size_t)g.vs * sizeof(double);
-  // fused stage kernels cover the dynamic variables; passives, the 8-wave / user sources and
+  // fused stage kernels cover the dynamic variables with the adiabatic equation of state; passives, the 8-wave / user sources and
   // eta != 0 (viscous_copy needs up's stale half-step ghosts) take the pass-per-routine kernels
-  s->fused = c->npas == 0 && !c->eight_wave && !c->user_source_terms && c->eta == 0.0 && !getenv("GX_NO_FUSED");
+  s->fused = c->npas == 0 && !c->eight_wave && !c->user_source_terms && c->eta == 0.0 && c->eq_of_state == GX_EOS_ADIABATIC && !getenv("GX_NO_FUSED");
   {
     // planes per CTA of the fused stage kernel: as long as possible (the z prologue costs 2*ORDER
     // plane loads and one extra z solve per chunk) while the grid still fills whole waves of SMs

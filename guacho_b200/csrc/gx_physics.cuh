@@ -103,14 +103,19 @@ __device__ __forceinline__ double sqrt_prod(const SqrtDen&, const SqrtDen&, doub
 // test is made warp-uniform with one vote, which keeps the override and its reconvergence bookkeeping out of the common
 // path (measured: -6 % on the second-order stage kernel); the strict build keeps the reference's plain per-lane tests.
 #if defined(GX_FLAVOUR_FAST) && !defined(GX_NO_VOTE_SUPERSONIC)
-#define GX_ANY_SUPERSONIC(sl, sr) __any_sync(__activemask(), ((sl) > 0.0) || ((sr) < 0.0))
+#ifndef GX_SOLVE_MASK            // lanes that solve together: the fused stage kernel solves with whole warps
+#define GX_SOLVE_MASK __activemask()
+#endif
+#define GX_ANY_SUPERSONIC(sl, sr) __any_sync(GX_SOLVE_MASK, ((sl) > 0.0) || ((sr) < 0.0))
 #else
 #define GX_ANY_SUPERSONIC(sl, sr) true
 #endif
 
 // ---- u2prim: src/hydro_core.f90:46-129 (dynamic variables only; passives are copies) ----
 // `pas0` is the first passive (needed by EOS_H_RATE only).
-template <bool MHD, bool WANT_T = true>
+// ADIABATIC: the caller guarantees eq_of_state == EOS_ADIABATIC (the fused stage kernels: gx_create routes every other
+// equation of state to the pass-per-routine kernels), so the temperature-floor branches and their divisions are not compiled.
+template <bool MHD, bool WANT_T = true, bool ADIABATIC = false>
 __device__ __forceinline__ void u2prim(const Phys& P, const double (&u)[8], double (&w)[8], double pas0, double& T) {
   double r = gx_max(u[0], 1e-15);
   w[0] = r;
@@ -130,7 +135,7 @@ __device__ __forceinline__ void u2prim(const Phys& P, const double (&u)[8], doub
   p = gx_max(p, 1e-16);
   if (MHD) { w[5] = u[5]; w[6] = u[6]; w[7] = u[7]; }
   T = 0.0;
-  if (P.eos == GX_EOS_ADIABATIC) {
+  if (ADIABATIC || P.eos == GX_EOS_ADIABATIC) {
     if (WANT_T) T = (p / r) * P.Tempsc;
   } else if (P.eos == GX_EOS_SINGLE_SPECIE) {
     double rr = gx_max(r, 1e-15);

@@ -22,6 +22,9 @@
 //   * face fluxes are exchanged through shared memory and the update is written with
 //     fully coalesced 256-byte row segments.
 // Compiled per (flavour, solver): -DGX_FLAVOUR_STRICT|-DGX_FLAVOUR_FAST, -DGX_STAGE_SOLVER=n.
+#ifndef GX_V_ACTIVEMASK
+#define GX_SOLVE_MASK 0xffffffffu   // every interface solve of this kernel is executed by all 32 lanes of a warp
+#endif
 #include "gx_kernels.cuh"
 
 #if defined(GX_FLAVOUR_STRICT)
@@ -138,11 +141,13 @@ __device__ __forceinline__ int solve_job(const gxp::Phys& P, const double* ring,
   gxp::PasInfo I;
   const int err = gxp::riemann<SOLVER>(P, wl, wr, fr, I);
   if (free_parity >= 0) mbar_wait(bar_free, free_parity);   // every warp has finished reading the previous plane's fluxes
-  if (J.store) {
-    double* o = xch + J.out;
+  {   // lanes of the closing warp that own no face write to a scratch word instead of branching around the stores
+    __shared__ double s_dummy[32];
+    double* o = J.store ? xch + J.out : s_dummy + (threadIdx.x & 31);
+    const int ovs = J.store ? J.ovs : 0;
     const int oc[8] = {0, J.on, J.ot1, J.ot2, 4, J.on + 4, J.ot1 + 4, J.ot2 + 4};
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) o[oc[q] * J.ovs] = fr[q];
+    for (int q = 0; q < NQ; ++q) o[oc[q] * ovs] = fr[q];
   }
   return J.check ? err : 0;
 }
@@ -175,7 +180,12 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
   // Ownership: a main-warp thread stages and converts ITS OWN centre cell (so its z solves, which
   // only read its own column, never wait for another thread), and the halo frame of the plane
   // (consumed ORDER+1 planes later by the x/y solves) is dealt round-robin.
+#ifndef GX_V_NO_VOTE_MAINWARP
+  // warp-uniform by construction; in the first-order kernel telling the compiler so (a vote) pays, in the second-order one it does not
+  const bool main_warp = (ORDER == 1) ? (bool)__all_sync(0xffffffffu, wrp < TY) : (wrp < TY);
+#else
   const bool main_warp = wrp < TY;
+#endif
   const int cidx = (min(wrp, TY - 1) + H) * CX + (lane + H);   // this thread's cell inside a staged plane
   constexpr int HC = PC - TY * TX;                       // halo cells of a staged plane
   auto halo_cell = [&](int h) {                          // h-th halo cell -> plane-local index
@@ -219,7 +229,7 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
     double u[8], w[8], T;
 #pragma unroll
     for (int q = 0; q < NQ; ++q) u[q] = sl[q * PC + c];
-    gxp::u2prim<MHD, false>(A.phys, u, w, 0.0, T);
+    gxp::u2prim<MHD, false, true>(A.phys, u, w, 0.0, T);
 #pragma unroll
     for (int q = 0; q < NQ; ++q) sl[q * PC + c] = w[q];
   };
@@ -266,13 +276,14 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
 #pragma unroll 1
     for (int jb = (xy ? 0 : 2); jb < njobs; ++jb) {
       FaceJob J;
-      if (jb == 0) {                                      // lower y face (extra warp: the row above the tile)
+      const int jt = jb == 0 ? 1 : (jb == 1 ? 0 : 2);     // job order: x face, y face, z face (measured marginally best)
+      if (jt == 0) {                                      // lower y face (extra warp: the row above the tile)
         const int c = sk + cidx + (main_warp ? 0 : CX);
         J.o_m2 = c - 2 * CX; J.o_m1 = c - CX; J.o_p0 = c; J.o_p1 = c + CX;
         J.on = 2; J.ot1 = 1; J.ot2 = 3;
         J.out = YB0 + wrp * TX + lane; J.ovs = YBV;
         J.store = true; J.check = (i <= g.nx && j <= g.ny + 1);
-      } else if (jb == 1) {                               // lower x face (extra warp: right of the last column, row = lane)
+      } else if (jt == 1) {                               // lower x face (extra warp: right of the last column, row = lane)
         const int row = main_warp ? wrp : min(lane, TY - 1), col = main_warp ? lane : TX;
         const int c = sk + (row + H) * CX + (col + H);
         J.o_m2 = c - 2; J.o_m1 = c - 1; J.o_p0 = c; J.o_p1 = c + 1;
@@ -327,7 +338,7 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
         E[2 * vs + c] = 0.25 * (-f6l - f6u + g5l + g5u);
       } else if (want_cfl) {                              // get_timestep candidates of the new state, hydro_core.f90:644-675
         double w[8], T;
-        gxp::u2prim<MHD, false>(A.phys, un, w, 0.0, T);
+        gxp::u2prim<MHD, false, true>(A.phys, un, w, 0.0, T);
         if (MHD) {
           double cx, cy, cz;
           gxp::cfast3(A.phys, w[4], w[0], w[5], w[6], w[7], cx, cy, cz);
