@@ -309,7 +309,7 @@ def main():
         "definition": "algorithmic bytes of the dominant kernel (read U* 8 + U^n 5, write U^{n+1} 5 + E 3 = 21 doubles per zone with flux-CD) x zones per GPU / its average launch time (CUDA events on the solver's stream)",
         "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak_gbs, "algorithmic_bytes_per_zone": bytes_zone,
                        "definition": "40*neq B per zone-update (5*neq doubles: 320 B MHD, 200 B hydro) x zones per GPU / whole-step device time"},
-        "fp64_note": "the kernel is FP64-pipe/latency bound, not HBM bound: see profiles/ (sm__inst_executed_pipe_fp64 ~43%, dram ~15%) and DESIGN.md",
+        "fp64_note": "the kernel is FP64-pipe/issue bound, not HBM bound: see profiles/ (sm__inst_executed_pipe_fp64 ~47%, issue ~56%, dram ~16%) and DESIGN.md",
         "kernel_share": {k: (v[0] / tot_prof if tot_prof > 0 else None) for k, v in ktimes.items() if v[1]},
         "kernel_ms_per_step": {k: v[0] / nprof for k, v in ktimes.items() if v[1]},
     }
