@@ -126,6 +126,9 @@ def cpu_reference(p_block: Params, steps: int, warmup: int, threads: int):
     per-zone work is identical), one block per thread like the reference's MPI ranks."""
     from tests.oracle_lib import Oracle
     nzs = 16
+    # one block per host thread, split along x like the reference's MPI ranks: the largest block count that
+    # divides the grid and leaves every block at least 4 cells wide (the host's core count need not divide 256)
+    threads = max(t for t in range(1, max(1, threads) + 1) if p_block.nxtot % t == 0 and p_block.nxtot // t >= 4)
     p = p_block.replace(nztot=nzs, zmax=p_block.zmax * nzs / p_block.nztot, MPI_NBX=threads, MPI_NBY=1, MPI_NBZ=1)
     o = Oracle(p, fast=True, threads=threads)
     g = problems.orszag_tang(p.replace(MPI_NBX=1), (0, 0, 0))
@@ -136,7 +139,7 @@ def cpu_reference(p_block: Params, steps: int, warmup: int, threads: int):
     sec = o.run_timed(steps)
     zones = p.nxtot * p.nytot * p.nztot
     sample = f"{p.nxtot}x{p.nytot}x{nzs} slab of the same OT field, {threads} blocks x 1 thread (x-split like the reference's MPI), {steps} steps after {max(1, warmup)} warm-up"
-    return zones * steps / sec, sec / steps * 1e3, sample
+    return zones * steps / sec, sec / steps * 1e3, sample, threads
 
 
 def run_reference(args):
@@ -146,7 +149,7 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     p = workload(args.n, 1)
     steps = max(1, min(args.steps, 3))
-    v, ms, sample = cpu_reference(p, steps, min(args.warmup, 1), threads)
+    v, ms, sample, threads = cpu_reference(p, steps, min(args.warmup, 1), threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -316,7 +319,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, _ms, sample = cpu_reference(workload(args.n, 1), 2, 1, threads)
+        v, _ms, sample, threads = cpu_reference(workload(args.n, 1), 2, 1, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
 
     line = {
