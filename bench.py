@@ -317,7 +317,7 @@ def main():
         "kernel_ms_per_step": {k: v[0] / nprof for k, v in ktimes.items() if v[1]},
     }
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:        # reported baseline: rank 0 at N = 1 only (bounded sample, a few seconds)
         threads = os.cpu_count() or 1
         v, _ms, sample, threads = cpu_reference(workload(args.n, 1), 2, 1, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
