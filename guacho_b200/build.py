@@ -81,6 +81,19 @@ def build_library(force: bool = False, verbose: bool = False, extra=(), out: str
     return out
 
 
+HOST_SRC = os.path.join(HERE, "host", "guacho_host.cpp")
+HOST_BIN = os.path.join(HERE, "host", "guacho_host")
+
+
+def build_host(force: bool = False) -> str:
+    """The compiled host driver (mirror of src/main.f90 over the C ABI): g++ only, links libguacho_gx.so."""
+    if not force and os.path.exists(HOST_BIN) and os.path.getmtime(HOST_BIN) >= max(os.path.getmtime(HOST_SRC), os.path.getmtime(LIB)):
+        return HOST_BIN
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", HOST_SRC, "-I" + os.path.join(os.path.dirname(HERE), "include"),
+                           "-L" + HERE, "-lguacho_gx", "-Wl,-rpath,$ORIGIN/..", "-o", HOST_BIN])
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     defs = [a for a in sys.argv[1:] if a.startswith("-D")]
     outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
