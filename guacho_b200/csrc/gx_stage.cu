@@ -9,22 +9,21 @@
 // cell-centred electric field) once.
 //
 // Structure (2.5-D marching, FP64 stencil):
-//   * a CTA owns a TX x TY = 32 x 10 column of cells and marches along z through KZ planes;
+//   * a CTA owns a TX x TY = 32 x 7 column of cells (8 warps, one CTA per SM: 296 CTAs = 2 per SM at 256^3) and
+//     marches along z through KZ planes;
 //   * conserved planes are staged into shared memory with cp.async (LDGSTS, 8-byte
 //     elements: tile rows start on odd 8-byte offsets once the halo is included) one
 //     plane ahead of the compute, converted in place to primitives, and kept in a ring
 //     of 2*ORDER planes (the z stencil) + 1 in flight;
 //   * warp r (< TY) owns row r of the tile, lane l owns cell i0+l.  Each thread solves the
-//     LOWER x face and LOWER y face of its cell and the UPPER z face (whose flux is
+//     LOWER x face, the LOWER y face of its cell and then the UPPER z face (whose flux is
 //     carried in registers to the next plane), so every interface is solved exactly once
 //     inside the tile; warp TY solves the tile's closing faces (the y faces above the
 //     last row, then the x faces right of the last column);
 //   * face fluxes are exchanged through shared memory and the update is written with
 //     fully coalesced 256-byte row segments.
 // Compiled per (flavour, solver): -DGX_FLAVOUR_STRICT|-DGX_FLAVOUR_FAST, -DGX_STAGE_SOLVER=n.
-#ifndef GX_V_ACTIVEMASK
 #define GX_SOLVE_MASK 0xffffffffu   // every interface solve of this kernel is executed by all 32 lanes of a warp
-#endif
 #include "gx_kernels.cuh"
 
 #if defined(GX_FLAVOUR_STRICT)
@@ -180,12 +179,8 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
   // Ownership: a main-warp thread stages and converts ITS OWN centre cell (so its z solves, which
   // only read its own column, never wait for another thread), and the halo frame of the plane
   // (consumed ORDER+1 planes later by the x/y solves) is dealt round-robin.
-#ifndef GX_V_NO_VOTE_MAINWARP
   // warp-uniform by construction; in the first-order kernel telling the compiler so (a vote) pays, in the second-order one it does not
   const bool main_warp = (ORDER == 1) ? (bool)__all_sync(0xffffffffu, wrp < TY) : (wrp < TY);
-#else
-  const bool main_warp = wrp < TY;
-#endif
   const int cidx = (min(wrp, TY - 1) + H) * CX + (lane + H);   // this thread's cell inside a staged plane
   constexpr int HC = PC - TY * TX;                       // halo cells of a staged plane
   auto halo_cell = [&](int h) {                          // h-th halo cell -> plane-local index

@@ -138,7 +138,7 @@ GX_API int gx_set_gravity_points(gx_solver* s, int32_t n, const double* gm, cons
 /* impose_user_bc as a device functor: conserved state re-imposed inside
  * spheres on every boundaryI/boundaryII call (EXO/exoplanet.f90:125-266).
  * Each sphere: centre, radius, radial wind speed, density, thermal term
- * cv*dens*T_eff, bulk velocity, dipole moment amplitude (b0 at radius), passive
+ * cv*dens*tfac*temp, bulk velocity, dipole moment amplitude (b0 at radius), passive
  * values per unit density.  See gx_wind_sphere. */
 #define GX_MAX_SPHERES 4
 typedef struct gx_wind_sphere {
