@@ -251,6 +251,14 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
   const int i = i0 + lane, j = j0 + wrp;
   const bool cell_ok = main_warp && i <= g.nx && j <= g.ny;
   const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
+  // plane-invariant parts of this thread's three face jobs (x: extra warp closes right of the last column, row = lane;
+  // y: extra warp closes the row above the tile)
+  const int row_x = main_warp ? wrp : min(lane, TY - 1), col_x = main_warp ? lane : TX;
+  const int cx_const = (row_x + H) * CX + (col_x + H), cy_const = cidx + (main_warp ? 0 : CX);
+  const int out_x = XB0 + row_x * (TX + 1) + col_x;
+  const bool store_x = main_warp || lane < TY;
+  const bool check_x = main_warp ? (i <= g.nx + 1 && j <= g.ny) : (lane < TY && i0 + TX <= g.nx + 1 && j0 + lane <= g.ny);
+  const bool check_y = (i <= g.nx && j <= g.ny + 1);
   double hprev[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) hprev[q] = 0.0;
@@ -266,37 +274,29 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
     // jobs of this thread: main warps solve the lower y face, the lower x face and the upper z face
     // of their cell; warp TY closes the tile (y faces above the last row, x faces right of the last column)
     const int njobs = main_warp ? 3 : 2;
+    const int sp1 = slot_off(k + 1), sm1 = (ORDER == 2) ? slot_off(k - 1) : sk, sp2 = (ORDER == 2) ? slot_off(k + 2) : sp1;
     double ub[8];
     const long long cg = g.idx(min(i, g.nx), min(j, g.ny), max(k, 1));
 #pragma unroll 1
     for (int jb = (xy ? 0 : 2); jb < njobs; ++jb) {
+      // branch-free job descriptor: the job type only steers selects (no divergent if/else chain per solve)
       FaceJob J;
-      const int jt = jb == 0 ? 1 : (jb == 1 ? 0 : 2);     // job order: x face, y face, z face (measured marginally best)
-      if (jt == 0) {                                      // lower y face (extra warp: the row above the tile)
-        const int c = sk + cidx + (main_warp ? 0 : CX);
-        J.o_m2 = c - 2 * CX; J.o_m1 = c - CX; J.o_p0 = c; J.o_p1 = c + CX;
-        J.on = 2; J.ot1 = 1; J.ot2 = 3;
-        J.out = YB0 + wrp * TX + lane; J.ovs = YBV;
-        J.store = true; J.check = (i <= g.nx && j <= g.ny + 1);
-      } else if (jt == 1) {                               // lower x face (extra warp: right of the last column, row = lane)
-        const int row = main_warp ? wrp : min(lane, TY - 1), col = main_warp ? lane : TX;
-        const int c = sk + (row + H) * CX + (col + H);
-        J.o_m2 = c - 2; J.o_m1 = c - 1; J.o_p0 = c; J.o_p1 = c + 1;
-        J.on = 1; J.ot1 = 2; J.ot2 = 3;
-        J.out = XB0 + row * (TX + 1) + col; J.ovs = XBV;
-        J.store = main_warp || lane < TY;
-        J.check = main_warp ? (i <= g.nx + 1 && j <= g.ny) : (lane < TY && i0 + TX <= g.nx + 1 && j0 + lane <= g.ny);
-      } else {                                            // upper z face: planes k-H+1 .. k+H, own column only
-        J.o_m1 = sk + cidx; J.o_p0 = slot_off(k + 1) + cidx;
-        J.o_m2 = (ORDER == 2) ? slot_off(k - 1) + cidx : J.o_m1;
-        J.o_p1 = (ORDER == 2) ? slot_off(k + 2) + cidx : J.o_p0;
-        J.on = 3; J.ot1 = 2; J.ot2 = 1;
-        J.out = ZB0 + wrp * TX + lane; J.ovs = ZBV;
-        J.store = true; J.check = cell_ok;
-        if (xy) {                                         // base state for the update: in flight during the z solve
+      const int jt = jb == 0 ? 1 : (jb == 1 ? 0 : 2);     // job order: x face, y face, z face
+      const bool isx = jt == 1, isz = jt == 2;
+      const int cxy = isx ? sk + cx_const : sk + cy_const;
+      const int st = isx ? 1 : CX;
+      J.o_p0 = isz ? sp1 + cidx : cxy;
+      J.o_m1 = isz ? sk + cidx : cxy - st;
+      J.o_m2 = isz ? ((ORDER == 2) ? sm1 + cidx : sk + cidx) : cxy - 2 * st;
+      J.o_p1 = isz ? ((ORDER == 2) ? sp2 + cidx : sp1 + cidx) : cxy + st;
+      J.on = isx ? 1 : (isz ? 3 : 2); J.ot1 = isx ? 2 : (isz ? 2 : 1); J.ot2 = isz ? 1 : 3;
+      J.out = isx ? out_x : (isz ? ZB0 : YB0) + wrp * TX + lane;
+      J.ovs = isx ? XBV : (isz ? ZBV : YBV);
+      J.store = isx ? store_x : true;
+      J.check = isx ? check_x : (isz ? cell_ok : check_y);
+      if (isz && xy) {                                    // base state for the update: in flight during the z solve
 #pragma unroll
-          for (int q = 0; q < NQ; ++q) if (!(FLUXCD && q >= 5)) ub[q] = Ub[q * vs + cg];
-        }
+        for (int q = 0; q < NQ; ++q) if (!(FLUXCD && q >= 5)) ub[q] = Ub[q * vs + cg];
       }
       J.vn = J.on * PC; J.vt1 = J.ot1 * PC; J.vt2 = J.ot2 * PC;
       // the first x/y store of a plane waits until every thread has consumed the previous plane's fluxes
