@@ -311,3 +311,57 @@ def test_cooling_atomic_cell_properties():
         yeq = (-b - np.sqrt(b * b - 4 * a * c)) / (2 * a)
         u_eq = o.cool_atomic(1.0e15, u)
         assert abs(u_eq[8] / u_eq[0] - min(yeq, 0.9999)) < 1e-9
+
+
+# ---- symmetry properties of the interface fluxes (all four solvers) ---------------------
+def _cons_of(o, w):
+    return o.prim2u(w)
+
+
+@pytest.mark.parametrize("solver,mhd", SOLVERS)
+def test_flux_scaling_invariance(solver, mhd):
+    """rho -> a rho, p -> a p, B -> sqrt(a) B at fixed velocity scales every wave speed by 1, so the mass, momentum
+    and energy fluxes scale by a and the induction fluxes by sqrt(a) (exactly, up to round-off), for a = 4 (sqrt exact)."""
+    o = Oracle(_par(solver, mhd))
+    W = _states(o.p.neq, 64, 11)
+    a = 4.0
+    for l, r in zip(W[::2], W[1::2]):
+        f, _ = o.riemann(l, r)
+        ls, rs = l.copy(), r.copy()
+        for s in (ls, rs):
+            s[0] *= a; s[4] *= a
+            if mhd:
+                s[5:8] *= 2.0
+        fs, _ = o.riemann(ls, rs)
+        scale = np.array([a] * 5 + ([2.0] * 3 if mhd else []))
+        assert np.abs(fs - scale * f).max() <= 1e-13 * (np.abs(scale * f).max() + 1.0)
+
+
+@pytest.mark.parametrize("solver", [SOLVER_HLL, SOLVER_HLLC])
+def test_flux_transverse_galilean_invariance(solver):
+    """Hydro: a boost along the interface leaves the wave fan unchanged, so the mass and normal-momentum fluxes are
+    unchanged and the transverse momentum flux gains v_boost x (mass flux) — exact consequences of Galilean invariance."""
+    o = Oracle(_par(solver, False))
+    W = _states(5, 64, 12)
+    for l, r in zip(W[::2], W[1::2]):
+        f, _ = o.riemann(l, r)
+        lt, rt = l.copy(), r.copy()
+        lt[2] += 0.7; rt[2] += 0.7
+        ft, _ = o.riemann(lt, rt)
+        assert abs(ft[0] - f[0]) <= 1e-13 * (abs(f[0]) + 1)
+        assert abs(ft[1] - f[1]) <= 1e-13 * (abs(f[1]) + 1)
+        assert abs(ft[2] - (f[2] + 0.7 * f[0])) <= 1e-13 * (abs(f[2]) + abs(f[0]) + 1)
+        assert abs(ft[3] - f[3]) <= 1e-13 * (abs(f[3]) + 1)
+
+
+def test_hlld_reduces_to_hllc_like_contact_when_field_vanishes():
+    """With B = 0 the HLLD fan collapses to the three-wave (HLLC) structure with the same Davis speeds: the mass,
+    momentum and energy fluxes of prim2fhlld (src/hlld.f90) and prim2fhllc (src/hllc.f90) must agree."""
+    od, oc = Oracle(_par(SOLVER_HLLD, True)), Oracle(_par(SOLVER_HLLC, False))
+    W = _states(8, 64, 13)
+    W[:, 5:8] = 0.0
+    for l, r in zip(W[::2], W[1::2]):
+        fd, _ = od.riemann(l, r)
+        fc, _ = oc.riemann(l[:5], r[:5])
+        assert np.abs(fd[:5] - fc).max() <= 1e-13 * (np.abs(fc).max() + 1)
+        assert np.abs(fd[5:]).max() == 0.0
