@@ -9,7 +9,13 @@
 // image, so the reference itself cannot be run here.  This
 // file restates the Fortran loop for loop (same AoS layout, same index ranges,
 // same operation order, same pack-all-then-exchange halo semantics) and is
-// pinned only by derived known-answer tests in tests/test_oracle_kat.py.
+// pinned by (a) tests/test_oracle_golden.py: fixtures computed from the
+// PUBLISHED form of each algorithm, independently of this file
+// (tests/golden/make_golden.py: Miyoshi-Kusano HLLD in jump-condition form,
+// HLL/HLLC, the exact Sod solution, the analytic first Orszag-Tang time step)
+// and frozen end-to-end outputs; (b) tests/test_oracle_kat.py: known answers
+// and invariants that follow from the reference code; (c) tests/test_bin_io.py:
+// the dump format through the reference's own Python reader.
 //
 // Build: g++ -O2 -ffp-contract=off (the reference is built -O3 without FMA
 // contraction on x86-64: OT/Makefile:24,115-123).  Every function cites the
