@@ -51,3 +51,41 @@ def test_no_gpu_means_loud_failure_not_fallback():
     rc = L.gx_create(C.byref(cfg), C.byref(h))
     assert rc == -2, (rc, L.gx_last_error())
     assert b"no CPU fallback" in L.gx_last_error()
+
+
+def test_product_path_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under guacho_b200/ may import, link or name it, and the shared
+    library must not depend on it (ldd) or carry its symbols."""
+    import subprocess
+    pkg = os.path.join(ROOT, "guacho_b200")
+    offenders = []
+    for dirpath, _dirs, files in os.walk(pkg):
+        if "build" in os.path.basename(dirpath):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".f90")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                if re.search(r"#include[^\n]*oracle|dlopen[^\n]*oracle|import[^\n]*oracle|from\s+tests|import\s+tests|libguacho_oracle|\borc_[a-z_]+\(", txt):
+                    offenders.append(os.path.join(dirpath, f))
+    assert offenders == []
+    if not os.path.exists(gxlib.LIB_PATH):
+        from guacho_b200.build import build_library
+        build_library()
+    deps = subprocess.run(["ldd", gxlib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in deps
+    syms = subprocess.run(["nm", "-D", "--defined-only", gxlib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "orc_" not in syms
+    exported = sorted(set(re.findall(r"\bT (gx_\w+)", syms)))
+    assert exported == sorted(gxlib.EXPORTS)          # nothing but the declared C ABI is exported (-fvisibility=hidden)
+
+
+def test_every_replaced_interface_cites_the_reference():
+    """include/guacho_gx.h: each entry point that replaces a reference interface says which one (file:line)."""
+    hdr = open(os.path.join(ROOT, "include", "guacho_gx.h")).read()
+    must_cite = ["gx_create", "gx_set_state", "gx_set_time", "gx_get_timestep", "gx_tstep", "gx_run", "gx_get_state",
+                 "gx_set_gravity_points", "gx_set_wind_spheres", "gx_register_bc_hook", "gx_comm_unique_id"]
+    for name in must_cite:
+        pos = hdr.index("GX_API int " + name + "(")
+        start = hdr.rfind("/*", 0, pos)
+        comment = hdr[start:pos]
+        assert re.search(r"\.f90:\d+", comment), f"{name}: no reference file:line in its comment"
