@@ -86,6 +86,6 @@ def test_every_replaced_interface_cites_the_reference():
                  "gx_set_gravity_points", "gx_set_wind_spheres", "gx_register_bc_hook", "gx_comm_unique_id"]
     for name in must_cite:
         pos = hdr.index("GX_API int " + name + "(")
-        start = hdr.rfind("/*", 0, pos)
-        comment = hdr[start:pos]
+        prev = hdr.rfind("GX_API", 0, pos)              # everything since the previous entry point: comment (+ typedefs)
+        comment = hdr[max(prev, 0):pos]
         assert re.search(r"\.f90:\d+", comment), f"{name}: no reference file:line in its comment"
