@@ -50,3 +50,17 @@ def test_host_driver_reproduces_the_python_host_bitwise(tmp_path):
         u, h = read_bin(os.path.join(tmp_path, "BIN", files[k]))
         assert h["n"] == (n, n, 2) and h["neq"] == 8 and h["nghost"] == 2 and h["mpi"] == (1, 1, 1)
         assert np.array_equal(u[..., 2:-2, 2:-2, 2:-2], ref[..., 2:-2, 2:-2, 2:-2]), k
+
+
+def test_python_runner_parses_and_refuses_without_a_gpu(tmp_path):
+    """guacho_b200.run_ot is the Python twin of the compiled host; without a CUDA device it must fail loudly."""
+    import torch
+    from guacho_b200 import run_ot
+    from guacho_b200.lib import GxError
+    a = run_ot.parse(["--grid", "64", "64", "2", "--tmax", "0.01", "--out", str(tmp_path)])
+    assert a.grid == [64, 64, 2] and a.tmax == 0.01 and a.blocks is None
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(GxError) as e:
+        run_ot.main(["--grid", "16", "16", "2", "--tmax", "0.001", "--out", str(tmp_path) + "/", "--quiet"])
+    assert e.value.code == -2
