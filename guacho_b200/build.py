@@ -87,7 +87,8 @@ HOST_BIN = os.path.join(HERE, "host", "guacho_host")
 
 def build_host(force: bool = False) -> str:
     """The compiled host driver (mirror of src/main.f90 over the C ABI): g++ only, links libguacho_gx.so."""
-    build_library()                      # no-op when the library is up to date
+    if not os.path.exists(LIB):
+        build_library()
     if not force and os.path.exists(HOST_BIN) and os.path.getmtime(HOST_BIN) >= max(os.path.getmtime(HOST_SRC), os.path.getmtime(LIB)):
         return HOST_BIN
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", HOST_SRC, "-I" + os.path.join(os.path.dirname(HERE), "include"),
