@@ -305,6 +305,24 @@ def main():
         pass
     bytes_zone = 40.0 * pb.neq                        # 5*neq doubles: 320 B (MHD), 200 B (hydro)
     step_gbs = bytes_zone * zones_rank / (step_ms * 1e-3) / 1e9
+    # second ceiling: FP64 instructions per zone-update (ncu, committed profile) against the measured DFMA
+    # issue rate of this GPU (profiles/peaks_r1.json) and all instructions against the issue slots at the sampled clock
+    fp64 = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tj2 = json.load(f)
+        with open(os.path.join(ROOT, "profiles", "peaks_r1.json")) as f:
+            pk = json.load(f)
+        if fused and args.solver == "hlld":
+            ceil_fp64 = pk["dfma_per_s"] / tj2["fp64_thread_inst_per_zone_update"]
+            sm_hz = 1e6 * (clocks or {}).get("sm_mhz", 1965.0) if (clocks or {}).get("sm_mhz") else 1.965e9
+            ceil_issue = pk["sms"] * 4 * 32 * sm_hz / tj2["thread_inst_per_zone_update"]
+            fp64 = {"fp64_inst_per_zone_update": tj2["fp64_thread_inst_per_zone_update"], "inst_per_zone_update": tj2["thread_inst_per_zone_update"],
+                    "dfma_per_s_measured": pk["dfma_per_s"], "fp64_ceiling_zone_updates_per_s": ceil_fp64, "frac_of_fp64_ceiling": value / world / ceil_fp64,
+                    "issue_ceiling_zone_updates_per_s": ceil_issue, "frac_of_issue_ceiling": value / world / ceil_issue,
+                    "note": "informational: the step is bound by FP64 issue, not HBM; instruction counts from the committed ncu capture"}
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm", "achieved": dom_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": (dom_gbs / peak_gbs if dom_gbs else None), "traffic": traffic,
         "peak_source": peak_src, "kernel": dom_name, "avg_launch_ms": dom_avg_ms,
@@ -313,6 +331,7 @@ def main():
         "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak_gbs, "algorithmic_bytes_per_zone": bytes_zone,
                        "definition": "40*neq B per zone-update (5*neq doubles: 320 B MHD, 200 B hydro) x zones per GPU / whole-step device time"},
         "fp64_note": "the kernel is FP64-pipe/issue bound, not HBM bound: see profiles/ (sm__inst_executed_pipe_fp64 ~47%, issue ~56%, dram ~16%) and DESIGN.md",
+        "fp64_issue": fp64,
         "kernel_share": {k: (v[0] / tot_prof if tot_prof > 0 else None) for k, v in ktimes.items() if v[1]},
         "kernel_ms_per_step": {k: v[0] / nprof for k, v in ktimes.items() if v[1]},
     }
