@@ -31,6 +31,7 @@ def parse(argv=None):
     ap.add_argument("--out", default="./")
     ap.add_argument("--strict", action="store_true", help="bit-comparison kernels (-fmad=false)")
     ap.add_argument("--divb", action="store_true", help="also dump div B (dump_divb in parameters.f90)")
+    ap.add_argument("--warm", type=int, default=None, metavar="ITPRINT0", help="iwarm: restart from BIN dump number ITPRINT0 under --out")
     ap.add_argument("--quiet", action="store_true")
     return ap.parse_args(argv)
 
@@ -57,9 +58,12 @@ def main(argv=None) -> int:
         if rank == 0 and not a.quiet:
             print(f"****************** wrote output *************** : {path}", flush=True)
 
-    sim.initflow(problems.orszag_tang(blk.p, coords))      # initflow -> boundaryI -> calcprim (main.f90:73-79)
-    dump(sim)                                              # main.f90:84-87: the initial condition is output 0 ...
-    sim.itprint = 1                                        # ... and itprint moves on
+    if a.warm is not None:                                 # iwarm (init.f90:134-142, 436-471): no output of the restart state
+        sim.warm_start(a.out, a.warm)
+    else:
+        sim.initflow(problems.orszag_tang(blk.p, coords))  # initflow -> boundaryI -> calcprim (main.f90:73-79)
+        dump(sim)                                          # main.f90:84-87: the initial condition is output 0 ...
+        sim.itprint = 1                                    # ... and itprint moves on
     sim.on_output = dump
     while sim.time <= p.tmax:                              # main.f90:94
         dt = sim.step()

@@ -210,6 +210,21 @@ class Simulation:
     def initflow(self, u: np.ndarray) -> None:
         self.b.set_state(u)
 
+    def warm_start(self, outputpath: str, itprint0: int) -> None:
+        """`iwarm = .true.`: restart from this block's BIN dump number `itprint0` (src/init.f90:134-142 sets
+        itprint = itprint0, time = itprint*dtprint, tprint = time + dtprint; :436-471 reads u with ghosts and moves
+        itprint on).  currentIteration restarts at 1, so the 10-step CFL ramp runs again, as in the reference."""
+        from .bin_io import bin_name, read_bin
+        u, hdr = read_bin(bin_name(outputpath, getattr(self.b, "rank", 0), itprint0))
+        if tuple(u.shape) != tuple(self.p.block_shape()):
+            raise ValueError(f"dump holds {u.shape}, this block is {self.p.block_shape()}")
+        self.itprint = itprint0
+        self.time = float(itprint0) * self.p.dtprint
+        self.tprint = self.time + self.p.dtprint
+        self.iteration = 1
+        self.b.set_state(u)
+        self.itprint += 1
+
     def step(self):
         dt, dump = self.b.get_timestep(self.iteration, self.n_iter_ramp, self.time, self.tprint)
         self.b.set_time(self.time)
