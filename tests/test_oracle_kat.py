@@ -365,3 +365,54 @@ def test_hlld_reduces_to_hllc_like_contact_when_field_vanishes():
         fc, _ = oc.riemann(l[:5], r[:5])
         assert np.abs(fd[:5] - fc).max() <= 1e-13 * (np.abs(fc).max() + 1)
         assert np.abs(fd[5:]).max() == 0.0
+
+
+# ---- decomposition invariance over a seeded matrix of solver / limiter / boundary / option combinations ----
+def _matrix():
+    rng = np.random.default_rng(2026)
+    bcs = [3, 1, 2]                       # periodic, outflow, closed
+    cases = []
+    for n in range(10):
+        solver, mhd = SOLVERS[rng.integers(0, 4)]
+        lim = int(rng.choice(ALL_LIMITERS))
+        bx, by, bz = (int(rng.choice(bcs)) for _ in range(3))
+        nb = [(2, 1, 1), (1, 2, 1), (1, 1, 2), (2, 2, 1), (1, 2, 2), (2, 1, 2)][rng.integers(0, 6)]
+        cd = bool(mhd and rng.integers(0, 2))
+        ew = bool(mhd and not cd and rng.integers(0, 2))
+        eta = 0.0                              # eta != 0 is decomposition-DEPENDENT in the reference: see the Q5 test below
+        npas = int(rng.integers(0, 3))
+        cases.append((solver, mhd, lim, bx, by, bz, nb, cd, ew, eta, npas))
+    return cases
+
+
+@pytest.mark.parametrize("case", _matrix(), ids=lambda c: "s%d-l%d-bc%d%d%d-nb%d%d%d-cd%d-ew%d-eta%g-p%d" % (c[0], c[2], c[3], c[4], c[5], *c[6], c[7], c[8], c[9], c[10]))
+def test_decomposition_invariance_matrix(case):
+    """Q1/Q2: interiors never read edge/corner ghosts, so any block decomposition reproduces the
+    single-block run bitwise — for every solver, limiter, boundary type, flux-CD / 8-wave and passives (eta = 0)."""
+    solver, mhd, lim, bx, by, bz, nb, cd, ew, eta, npas = case
+    p1 = Params(nxtot=12, nytot=8, nztot=8, zmax=1.0, mhd=mhd, riemann_solver=solver, slope_limiter=lim, enable_flux_cd=cd,
+                eight_wave=ew, eta=eta, npas=npas, bc_left=bx, bc_right=bx, bc_bottom=by, bc_top=by, bc_out=bz, bc_in=bz)
+    g = global_ic(p1, "random")
+    a = oracle_from_ic(p1, g, threads=1)
+    b = oracle_from_ic(p1.replace(MPI_NBX=nb[0], MPI_NBY=nb[1], MPI_NBZ=nb[2]), g, threads=4)
+    da, db = a.advance(3), b.advance(3)
+    assert da == db
+    assert np.array_equal(a.gather(U), b.gather(U))
+
+
+def test_viscosity_makes_the_reference_decomposition_dependent():
+    """viscous_copy (src/hydro_solver.f90:54-63) reads `up` ghosts that still hold the HALF-step halo set by
+    boundaryII, while inside a block the same neighbour holds the full-step value.  With eta != 0 the reference's
+    result therefore depends on where the block boundaries are — restated as is: the 2-block run differs from the
+    1-block run exactly in the cells next to the new internal face after one step, and nowhere else."""
+    p1 = Params(nxtot=12, nytot=8, nztot=8, zmax=1.0, enable_flux_cd=False, eta=0.01)
+    g = global_ic(p1, "random")
+    a = oracle_from_ic(p1, g, threads=1)
+    b = oracle_from_ic(p1.replace(MPI_NBZ=2), g, threads=2)
+    dt, _ = a.get_timestep(1, 10, 0.0, 1e300)
+    assert b.get_timestep(1, 10, 0.0, 1e300)[0] == dt
+    assert a.tstep(dt) == 0 and b.tstep(dt) == 0
+    d = np.abs(a.gather(U) - b.gather(U)).max(axis=(0, 1, 2))          # per z plane
+    touched = np.nonzero(d > 0)[0].tolist()
+    assert touched == [3, 4]      # the planes next to the new internal face; the domain's periodic face reads stale ghosts in both runs
+    assert d.max() < 1e-3 * np.abs(a.gather(U)).max()                  # an O(eta * dt) effect
