@@ -580,7 +580,7 @@ int gx_create(const gx_config* c, gx_solver** out) {
   g.cx = c->cx; g.cy = c->cy; g.cz = c->cz;
   g.nxtot = c->nxtot; g.nytot = c->nytot; g.nztot = c->nztot;
   g.dx = c->dx; g.dy = c->dy; g.dz = c->dz;
-  s->A.phys.cv = c->cv; s->A.phys.gamma = c->gamma; s->A.phys.Tempsc = c->Tempsc; s->A.phys.inv_cv = 1.0 / c->cv;
+  s->A.phys.cv = c->cv; s->A.phys.gamma = c->gamma; s->A.phys.Tempsc = c->Tempsc; s->A.phys.inv_cv = 1.0 / c->cv; s->A.phys.m4gamma = -4.0 * c->gamma;
   s->A.phys.eos = c->eq_of_state; s->A.phys.neqdyn = c->neqdyn; s->A.phys.npas = c->npas;
   s->A.solver = c->riemann_solver; s->A.limiter = c->slope_limiter;
   s->A.flux_cd = c->enable_flux_cd; s->A.eight_wave = c->eight_wave; s->A.user_src = c->user_source_terms;

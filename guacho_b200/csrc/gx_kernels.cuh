@@ -70,7 +70,7 @@ struct KernelTable {
 #define GX_STAGE_TX 32
 #endif
 #ifndef GX_STAGE_TY
-#define GX_STAGE_TY 7
+#define GX_STAGE_TY 11
 #endif
 const KernelTable* kernels_strict();
 const KernelTable* kernels_fast();

@@ -17,6 +17,7 @@ namespace gxp {
 struct Phys {            // the scalar `parameter`s the cell routines read
   double cv, gamma, Tempsc;
   double inv_cv;         // 1/cv (fast build: p = (...)*inv_cv instead of an IEEE division)
+  double m4gamma;        // -4 gamma (fast build: discriminant of the fast speed)
   int eos;               // GX_EOS_*
   int neqdyn, npas;      // neq = neqdyn + npas
 };
@@ -49,27 +50,20 @@ __device__ __forceinline__ double fast_rcp(double x) {
   double t = fma(e, e, e);                                    // e + e^2
   return fma(r, t, r);                                        // error ~ e^3 = 2^-69
 }
-// s = sqrt(x), rs = 1/sqrt(x) for x > 0 (callers guarantee x > 0: densities, or a discriminant
-// clamped to a tiny positive number).  MUFU.RSQ64H seed (2^-22) + two coupled Newton steps.
-__device__ __forceinline__ void fast_sqrt_rsqrt(double x, double& s, double& rs) {
+// 1/sqrt(x) for x > 0 (callers guarantee x > 0: densities, or a discriminant clamped to a tiny positive number).
+// MUFU.RSQ64H seed y (rel. error d <= 2^-22) and ONE third-order step: with e = 1 - x y^2 (= -2d),
+// 1/sqrt(x) = y (1 - e)^(-1/2) = y (1 + e/2 + 3 e^2/8 + 5 e^3/16 ...): the truncation error 5/16 e^3 is below 2^-64.
+// Five FP64 instructions after the seed (two coupled Newton steps cost eight).
+__device__ __forceinline__ double fast_rsqrt(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double g = x * y, h = 0.5 * y;
-  double r = fma(-h, g, 0.5);
-  g = fma(g, r, g); h = fma(h, r, h);
-  r = fma(-h, g, 0.5);
-  s = fma(g, r, g);
-  rs = 2.0 * fma(h, r, h);
+  const double t = x * y;
+  const double e = fma(-t, y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  return fma(y, e * p, y);
 }
-__device__ __forceinline__ double gx_sqrt(double x) {     // sqrt only: the last step needs no updated h
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double g = x * y, h = 0.5 * y;
-  double r = fma(-h, g, 0.5);
-  g = fma(g, r, g); h = fma(h, r, h);
-  r = fma(-h, g, 0.5);
-  return fma(g, r, g);
-}
+__device__ __forceinline__ void fast_sqrt_rsqrt(double x, double& s, double& rs) { rs = fast_rsqrt(x); s = x * rs; }
+__device__ __forceinline__ double gx_sqrt(double x) { return x * fast_rsqrt(x); }
 // discriminant of the fast-speed formula: >= 0 analytically, may round to -eps (or be exactly 0)
 __device__ __forceinline__ double gx_sqrt_disc(double x) { return gx_sqrt(gx_max(x, 1e-300)); }
 struct Den {                      // a denominator used one or more times
@@ -150,6 +144,40 @@ __device__ __forceinline__ void u2prim(const Phys& P, const double (&u)[8], doub
 }
 
 // ---- wave speeds: src/hydro_core.f90:544-604 ----
+#if defined(GX_FLAVOUR_FAST)
+// Production forms: no division at all.  With g = gamma p + B^2 and D = g^2 - 4 gamma p Bn^2 (rho^2 times the
+// reference's discriminant), cf^2 = (g + sqrt D) / (2 rho) =: N / (2 rho), so cf = N / sqrt(2 rho N): two
+// reciprocal square roots (MUFU seed + one third-order step each) instead of a reciprocal and two square roots.
+__device__ __forceinline__ double csound(const Phys& P, double p, double d) {
+  const double gp = P.gamma * p;
+  return gp * fast_rsqrt(gp * d);                                  // sqrt(gamma p / rho)
+}
+// g2 = g*g, m4gp = -4 gamma p, rho2 = 2 rho, bn2 = Bn^2
+__device__ __forceinline__ double cfast_from(double g, double g2, double m4gp, double rho2, double bn2) {
+  const double x = fabs(fma(m4gp, bn2, g2)) + 1e-300;              // D >= 0 analytically; may round to -eps or be exactly 0
+  const double n = fma(x, fast_rsqrt(x), g);                       // N = g + sqrt D
+  return n * fast_rsqrt(rho2 * n);
+}
+// bt2 = sum of the squares of the two transverse field components (shared with the total pressure in HLLD)
+__device__ __forceinline__ double cfast_dir(const Phys& P, double rho, double p, double bn, double bt2) {
+  const double bn2 = bn * bn;
+  const double g = fma(P.gamma, p, bn2) + bt2;
+  return cfast_from(g, g * g, P.m4gamma * p, rho + rho, bn2);
+}
+__device__ __forceinline__ double cfastX(const Phys& P, const double (&w)[8]) {
+  return cfast_dir(P, w[0], w[4], w[5], fma(w[7], w[7], w[6] * w[6]));
+}
+// CFL form (src/hydro_core.f90:568-581): fast speed along each axis
+__device__ __forceinline__ void cfast3(const Phys& P, double p, double d, double bx, double by, double bz,
+                                       double& cx, double& cy, double& cz) {
+  const double bx2 = bx * bx, by2 = by * by, bz2 = bz * bz;
+  const double g = fma(P.gamma, p, bx2) + (by2 + bz2);
+  const double g2 = g * g, m4gp = P.m4gamma * p, rho2 = d + d;
+  cx = cfast_from(g, g2, m4gp, rho2, bx2);
+  cy = cfast_from(g, g2, m4gp, rho2, by2);
+  cz = cfast_from(g, g2, m4gp, rho2, bz2);
+}
+#else
 __device__ __forceinline__ double csound(const Phys& P, double p, double d) { return gx_sqrt(Den(d).div(P.gamma * p)); }
 
 __device__ __forceinline__ double cfastX(const Phys& P, const double (&w)[8]) {
@@ -169,6 +197,26 @@ __device__ __forceinline__ void cfast3(const Phys& P, double p, double d, double
   cx = gx_sqrt(dd.div(0.5 * (gpb + gx_sqrt_disc(gpb * gpb - gp4 * bx * bx))));
   cy = gx_sqrt(dd.div(0.5 * (gpb + gx_sqrt_disc(gpb * gpb - gp4 * by * by))));
   cz = gx_sqrt(dd.div(0.5 * (gpb + gx_sqrt_disc(gpb * gpb - gp4 * bz * bz))));
+}
+#endif
+
+// Signal speeds of one CELL for the first-order stage, where the states either side of a face are cell values: the
+// reference evaluates csound / cfastX per side per face (hll.f90:57-58, hlle.f90:58-59, hlld.f90:64-65), i.e. six
+// times per cell and stage; the same function of the same cell state gives the same bits, so the fused stage kernel
+// evaluates it once per cell and direction.  c[d] = speed along x, y, z (hydro solvers: c[0] only).
+template <bool MHD>
+__device__ __forceinline__ void cell_speeds(const Phys& P, const double (&w)[8], double (&c)[3]) {
+  if (!MHD) { c[0] = csound(P, w[4], w[0]); c[1] = c[2] = 0.0; return; }
+#if defined(GX_FLAVOUR_FAST)
+  // same instruction sequence as cfast_dir for each direction (bt2 = the other two squares, y and z in storage order)
+  c[0] = cfast_dir(P, w[0], w[4], w[5], fma(w[7], w[7], w[6] * w[6]));
+  c[1] = cfast_dir(P, w[0], w[4], w[6], fma(w[7], w[7], w[5] * w[5]));
+  c[2] = cfast_dir(P, w[0], w[4], w[7], fma(w[5], w[5], w[6] * w[6]));
+#else
+  { const double r[8] = {w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]}; c[0] = cfastX(P, r); }
+  { const double r[8] = {w[0], w[2], w[1], w[3], w[4], w[6], w[5], w[7]}; c[1] = cfastX(P, r); }   // swapy
+  { const double r[8] = {w[0], w[3], w[2], w[1], w[4], w[7], w[6], w[5]}; c[2] = cfastX(P, r); }   // swapz
+#endif
 }
 
 // ---- prim2f / prim2u: src/hydro_core.f90:331-476 (non-split branches) ----
@@ -288,12 +336,14 @@ __device__ __forceinline__ double passive_flux(const PasInfo& I, double ql, doub
   return 0.;
 }
 
+// Every solver takes the signal speeds of the two states as arguments (csound for HLL/HLLC, cfastX for HLLE/HLLD:
+// hll.f90:57-58, hllc.f90:55-56, hlle.f90:58-59, hlld.f90:64-65): the second-order sweeps evaluate them from the
+// reconstructed states, the first-order stage of the fused kernel reads the per-cell values (cell_speeds above).
+
 // ---- HLL (hydro speeds) / HLLE (fast speeds): src/hll.f90:47-82, src/hlle.f90:48-83 ----
-template <bool MHD, bool FAST>
-__device__ __forceinline__ int riemann_hll(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
-  double csl, csr;
-  if (FAST) { csl = cfastX(P, wl); csr = cfastX(P, wr); }
-  else { csl = csound(P, wl[4], wl[0]); csr = csound(P, wr[4], wr[0]); }
+template <bool MHD>
+__device__ __forceinline__ int riemann_hll(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I,
+                                           double csl, double csr) {
   double sr = gx_max(wl[1] + csl, wr[1] + csr);
   double sl = gx_min(wl[1] - csl, wr[1] - csr);
   I.ul = wl[1]; I.ur = wr[1]; I.sl = sl; I.sr = sr;
@@ -313,9 +363,8 @@ __device__ __forceinline__ int riemann_hll(const Phys& P, const double (&wl)[8],
 }
 
 // ---- HLLC: src/hllc.f90:44-140 (hydro) ----
-__device__ __forceinline__ int riemann_hllc_ref(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
-  double csl = csound(P, wl[4], wl[0]);
-  double csr = csound(P, wr[4], wr[0]);
+__device__ __forceinline__ int riemann_hllc_ref(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I,
+                                                double csl, double csr) {   // csl, csr = csound of either side (hllc.f90:55-56)
   double sr = gx_max(wl[1] + csl, wr[1] + csr);
   double sl = gx_min(wl[1] - csl, wr[1] - csr);
   I.ul = wl[1]; I.ur = wr[1]; I.sl = sl; I.sr = sr;
@@ -362,11 +411,10 @@ __device__ __forceinline__ int riemann_hllc_ref(const Phys& P, const double (&wl
 
 #if defined(GX_FLAVOUR_FAST)
 // Production HLLC: the same expressions as riemann_hllc_ref / src/hllc.f90:44-140 in one basic block — the side K
-// that supplies the star state (L for S* >= 0, R otherwise) is chosen by selects, the four divisions become
-// Newton-refined reciprocals (1/rho_K shared), and the two supersonic cases are a rare override at the end.
-__device__ __forceinline__ int riemann_hllc(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
-  const double irl = fast_rcp(wl[0]), irr = fast_rcp(wr[0]);
-  const double csl = gx_sqrt(P.gamma * wl[4] * irl), csr = gx_sqrt(P.gamma * wr[4] * irr);
+// that supplies the star state (L for S* >= 0, R otherwise) is chosen by selects, the divisions become
+// Newton-refined reciprocals, and the two supersonic cases are a rare override at the end.
+__device__ __forceinline__ int riemann_hllc(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I,
+                                            double csl, double csr) {
   const double sr = gx_max(wl[1] + csl, wr[1] + csr);
   const double sl = gx_min(wl[1] - csl, wr[1] - csr);
   I.ul = wl[1]; I.ur = wr[1]; I.sl = sl; I.sr = sr;
@@ -376,10 +424,12 @@ __device__ __forceinline__ int riemann_hllc(const Phys& P, const double (&wl)[8]
   const bool left = sst >= 0.;
   const int err = (!left && !(sst <= 0.)) ? 1 : 0;                                               // NaN: 'Error in hllc' + stop (:135-138)
   const double q0 = left ? wl[0] : wr[0], q1 = left ? wl[1] : wr[1], q2 = left ? wl[2] : wr[2], q3 = left ? wl[3] : wr[3], q4 = left ? wl[4] : wr[4];
-  const double sK = left ? sl : sr, sKmu = left ? slmul : srmur, mK = left ? mL : mR, irK = left ? irl : irr;
+  const double sK = left ? sl : sr, mK = left ? mL : mR;
   const double rhost = mK * fast_rcp(sK - sst);                                                  // :80, :108
   const double ek = 0.5 * q0 * (q1 * q1 + q2 * q2 + q3 * q3) + P.cv * q4;
-  const double uk4 = rhost * (ek * irK + (sst - q1) * (sst + q4 * fast_rcp(mK)));                // :86-87
+  // ek / rho_K + (S* - u_K)(S* + p_K / m_K) with ONE reciprocal: 1/(rho_K m_K) serves both quotients
+  const double irm = fast_rcp(q0 * mK);
+  const double uk4 = rhost * ((ek * mK) * irm + (sst - q1) * (sst + (q4 * q0) * irm));           // :86-87
   const double m1 = q0 * q1;                                                                     // prim2f / prim2u of side K
   ff[0] = m1 + sK * (rhost - q0);
   ff[1] = (m1 * q1 + q4) + sK * (rhost * sst - m1);
@@ -387,7 +437,6 @@ __device__ __forceinline__ int riemann_hllc(const Phys& P, const double (&wl)[8]
   ff[3] = m1 * q3 + sK * (rhost * q3 - q0 * q3);
   ff[4] = q1 * (ek + q4) + sK * (uk4 - ek);
   I.mode = left ? PAS_HLLC_L : PAS_HLLC_R; I.a = rhost; I.b = q0;
-  (void)sKmu;
   if (GX_ANY_SUPERSONIC(sl, sr)) {
     if (sl > 0) { prim2f<false>(P, wl, ff); I.mode = PAS_UPL; return 0; }
     if (sr < 0) { prim2f<false>(P, wr, ff); I.mode = PAS_UPR; return 0; }
@@ -395,8 +444,9 @@ __device__ __forceinline__ int riemann_hllc(const Phys& P, const double (&wl)[8]
   return err;
 }
 #else
-__device__ __forceinline__ int riemann_hllc(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
-  return riemann_hllc_ref(P, wl, wr, ff, I);
+__device__ __forceinline__ int riemann_hllc(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I,
+                                            double csl, double csr) {
+  return riemann_hllc_ref(P, wl, wr, ff, I, csl, csr);
 }
 #endif
 
@@ -423,9 +473,8 @@ __device__ __forceinline__ double hlld_energy(const Phys& P, const double (&q)[8
   return 0.5 * q[0] * (q[1] * q[1] + q[2] * q[2] + q[3] * q[3]) + P.cv * q[4] + 0.5 * (bx * bx + q[6] * q[6] + q[7] * q[7]);
 }
 
-__device__ __forceinline__ int riemann_hlld_ref(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
-  double csl = cfastX(P, wl);
-  double csr = cfastX(P, wr);
+__device__ __forceinline__ int riemann_hlld_ref(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I,
+                                                double csl, double csr) {   // csl, csr = cfastX of either side (hlld.f90:64-65)
   double sr = gx_max(wl[1] + csl, wr[1] + csr);
   double sl = gx_min(wl[1] - csl, wr[1] - csr);
   I.ul = wl[1]; I.ur = wr[1]; I.sl = sl; I.sr = sr;
@@ -511,45 +560,45 @@ __device__ __forceinline__ int riemann_hlld_ref(const Phys& P, const double (&wl
 __device__ __forceinline__ double mul_sign(double x, double s) {
   return __hiloint2double(__double2hiint(x) ^ (__double2hiint(s) & 0x80000000), __double2loint(x));
 }
-// Straight-line (select-based) HLLD for the production build: the same expressions as
-// riemann_hlld_ref / src/hlld.f90:48-319, but both star states and the double-star blend are
-// always formed and the region (UL*, UL**, UR**, UR*) is chosen by selects.  One basic block
-// lets ptxas interleave the independent L/R chains (the kernel is FP64-latency bound, not
-// FP64-throughput bound); the two supersonic cases are a rare override at the end.
-__device__ __forceinline__ int riemann_hlld(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
-  const double csl = cfastX(P, wl), csr = cfastX(P, wr);
+// Straight-line (select-based) HLLD for the production build: the same quantities as riemann_hlld_ref /
+// src/hlld.f90:48-319 — both star states and the double-star blend are always formed and the region
+// (UL*, UL**, UR**, UR*) is chosen by selects, so the whole solve is one basic block whose independent L/R chains
+// ptxas interleaves; the two supersonic cases are a rare override at the end.  Division- and square-root-free:
+//   * rho*_K = m_K / (S_K - S_M), m_K = rho_K (S_K - u_K).  With x_K = m_K (S_K - S_M) > 0 and r_K = 1/sqrt(x_K):
+//     sqrt(rho*_K) = |m_K| r_K,  1/sqrt(rho*_K) = |S_K - S_M| r_K,  rho*_K = (|m_K| r_K)^2, and x_K - Bx^2 is the
+//     denominator of the star state (hlld.f90:117, 165) — one reciprocal square root per side instead of a
+//     reciprocal plus a square root;
+//   * 1/(S_K - S_M) is only needed for the energy of the side that supplies the flux: one reciprocal after the select.
+__device__ __forceinline__ int riemann_hlld(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I,
+                                            double csl, double csr, double bt2L, double bt2R) {   // bt2_K = By_K^2 + Bz_K^2
   const double sr = gx_max(wl[1] + csl, wr[1] + csr);
   const double sl = gx_min(wl[1] - csl, wr[1] - csr);
   I.ul = wl[1]; I.ur = wr[1]; I.sl = sl; I.sr = sr;
 
   const double bx = 0.5 * (wl[5] + wr[5]);
   const double bx2 = bx * bx;
-  const double pTL = wl[4] + 0.5 * (bx2 + wl[6] * wl[6] + wl[7] * wl[7]);
-  const double pTR = wr[4] + 0.5 * (bx2 + wr[6] * wr[6] + wr[7] * wr[7]);
+  const double pTL = fma(0.5, bx2 + bt2L, wl[4]), pTR = fma(0.5, bx2 + bt2R, wr[4]);
   const double slmul = sl - wl[1], srmur = sr - wr[1];
   const double mL = wl[0] * slmul, mR = wr[0] * srmur;            // rho_K (S_K - u_K)
   const double iden = fast_rcp(mR - mL);
   const double sM = (mR * wr[1] - mL * wl[1] - pTR + pTL) * iden;
   const double slmsM = sl - sM, srmsM = sr - sM;
-  const double islm = fast_rcp(slmsM), isrm = fast_rcp(srmsM);
-  const double rhostl = mL * islm, rhostr = mR * isrm;
-  double sql, rsql, sqr, rsqr;
-  fast_sqrt_rsqrt(rhostl, sql, rsql);
-  fast_sqrt_rsqrt(rhostr, sqr, rsqr);
+  const double xL = mL * slmsM, xR = mR * srmsM;                  // rho*_K (S_K - S_M)^2
+  const double rL = fast_rsqrt(xL), rR = fast_rsqrt(xR);
+  const double sql = fabs(mL) * rL, sqr = fabs(mR) * rR;          // sqrt(rho*_K)
   const double abx = fabs(bx);
-  const double sstl = sM - abx * rsql, sstr = sM + abx * rsqr;
+  const double sstl = fma(-(abx * fabs(slmsM)), rL, sM), sstr = fma(abx * fabs(srmsM), rR, sM);   // S*_K = S_M -+ |Bx| / sqrt(rho*_K)
   const double pst = (mR * pTL - mL * pTR + mL * mR * (wr[1] - wl[1])) * iden;
 
   // star states of both sides (hlld.f90:116-135, 164-183), degenerate guard by select
-  const double dL = mL * slmsM - bx2, dR = mR * srmsM - bx2;
+  const double dL = xL - bx2, dR = xR - bx2;
   const double rL_ = fast_rcp(dL), rR_ = fast_rcp(dR);
   // hlld.f90:119-126: den == 0 -> v* = v, w* = w, By* = Bz* = 0, which is what 1/den := 0 produces below
   const double idL = (dL != 0.0) ? rL_ : 0.0, idR = (dR != 0.0) ? rR_ : 0.0;
-  const double sMuL = sM - wl[1], sMuR = sM - wr[1];
-  const double cL = bx * sMuL * idL, cR = bx * sMuR * idR;         // Bx (S_M - u_K) / den_K
-  const double nL = (wl[0] * (slmul * slmul) - bx2) * idL, nR = (wr[0] * (srmur * srmur) - bx2) * idR;
-  const double vL = wl[2] - wl[6] * cL, wLs = wl[3] - wl[7] * cL;
-  const double vR = wr[2] - wr[6] * cR, wRs = wr[3] - wr[7] * cR;
+  const double cL = bx * (sM - wl[1]) * idL, cR = bx * (sM - wr[1]) * idR;          // Bx (S_M - u_K) / den_K
+  const double nL = fma(mL, slmul, -bx2) * idL, nR = fma(mR, srmur, -bx2) * idR;    // (rho_K (S_K - u_K)^2 - Bx^2) / den_K
+  const double vL = fma(-wl[6], cL, wl[2]), wLs = fma(-wl[7], cL, wl[3]);
+  const double vR = fma(-wr[6], cR, wr[2]), wRs = fma(-wr[7], cR, wr[3]);
   const double byL = wl[6] * nL, bzL = wl[7] * nL;
   const double byR = wr[6] * nR, bzR = wr[7] * nR;
 
@@ -569,21 +618,21 @@ __device__ __forceinline__ int riemann_hlld(const Phys& P, const double (&wl)[8]
 
   // outer state K = L | R by select, then one energy evaluation (hlld.f90:113-114, 137-156)
   const double q0 = left ? wl[0] : wr[0], q1 = left ? wl[1] : wr[1], q2 = left ? wl[2] : wr[2], q3 = left ? wl[3] : wr[3];
-  const double q4 = left ? wl[4] : wr[4], q6 = left ? wl[6] : wr[6], q7 = left ? wl[7] : wr[7];
-  const double sKmu = left ? slmul : srmur, iK = left ? islm : isrm, pTK = left ? pTL : pTR;
-  const double rhost = left ? rhostl : rhostr;
+  const double q4 = left ? wl[4] : wr[4], q6 = left ? wl[6] : wr[6], q7 = left ? wl[7] : wr[7], bt2K = left ? bt2L : bt2R;
+  const double sKmu = left ? slmul : srmur, sKmsM = left ? slmsM : srmsM, pTK = left ? pTL : pTR;
   const double vK = left ? vL : vR, wK = left ? wLs : wRs, byK = left ? byL : byR, bzK = left ? bzL : bzR;
   const double sqK = left ? -sql : sqr;
-  const double eK = 0.5 * q0 * (q1 * q1 + q2 * q2 + q3 * q3) + P.cv * q4 + 0.5 * (bx2 + q6 * q6 + q7 * q7);
+  const double iK = fast_rcp(sKmsM);
+  const double eK = 0.5 * q0 * (q1 * q1 + q2 * q2 + q3 * q3) + P.cv * q4 + 0.5 * (bx2 + bt2K);
   const double vdotb = q1 * bx + q2 * q6 + q3 * q7;
   const double vsdotbs = sM * bx + vK * byK + wK * bzK;
   const double estK = (sKmu * eK - pTK * q1 + pst * sM + bx * (vdotb - vsdotbs)) * iK;
   const double es = dstar ? estK + sqK * mul_sign(vsdotbs - vdb_ss, bx) : estK;
   const double vs = dstar ? vss : vK, ws = dstar ? wss : wK, bys = dstar ? byss : byK, bzs = dstar ? bzss : bzK;
   const double vdb = dstar ? vdb_ss : vsdotbs;
-  I.mode = left ? PAS_HLLD_L : PAS_HLLD_R; I.a = sM; I.b = sKmu; I.c = left ? slmsM : srmsM;
+  I.mode = left ? PAS_HLLD_L : PAS_HLLD_R; I.a = sM; I.b = sKmu; I.c = sKmsM;
 
-  const double rsm = rhost * sM;
+  const double rsm = (sqK * sqK) * sM;                              // rho*_K S_M
   ff[0] = rsm;
   ff[1] = rsm * sM + pst - bx2;
   ff[2] = rsm * vs - bx * bys;
@@ -600,18 +649,33 @@ __device__ __forceinline__ int riemann_hlld(const Phys& P, const double (&wl)[8]
   }
   return err;
 }
-#else
-__device__ __forceinline__ int riemann_hlld(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
-  return riemann_hlld_ref(P, wl, wr, ff, I);
-}
 #endif
 
-template <int SOLVER>
-__device__ __forceinline__ int riemann(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I) {
-  if (SOLVER == GX_SOLVER_HLL) return riemann_hll<false, false>(P, wl, wr, ff, I);
-  if (SOLVER == GX_SOLVER_HLLE) return riemann_hll<true, true>(P, wl, wr, ff, I);
-  if (SOLVER == GX_SOLVER_HLLC) return riemann_hllc(P, wl, wr, ff, I);
-  return riemann_hlld(P, wl, wr, ff, I);
+// Riemann flux of solver SOLVER.  PRE: csl / csr hold the signal speeds of the two states (first-order stage, cell_speeds);
+// otherwise they are evaluated here from wl / wr.
+template <int SOLVER, bool PRE = false>
+__device__ __forceinline__ int riemann(const Phys& P, const double (&wl)[8], const double (&wr)[8], double (&ff)[8], PasInfo& I,
+                                       double csl = 0.0, double csr = 0.0) {
+  constexpr bool FASTSPEED = (SOLVER == GX_SOLVER_HLLE || SOLVER == GX_SOLVER_HLLD);
+#if defined(GX_FLAVOUR_FAST)
+  if (SOLVER == GX_SOLVER_HLLD) {
+    const double bt2L = fma(wl[7], wl[7], wl[6] * wl[6]), bt2R = fma(wr[7], wr[7], wr[6] * wr[6]);
+    if (!PRE) { csl = cfast_dir(P, wl[0], wl[4], wl[5], bt2L); csr = cfast_dir(P, wr[0], wr[4], wr[5], bt2R); }
+    return riemann_hlld(P, wl, wr, ff, I, csl, csr, bt2L, bt2R);
+  }
+#endif
+  if (!PRE) {
+    if (FASTSPEED) { csl = cfastX(P, wl); csr = cfastX(P, wr); }
+    else { csl = csound(P, wl[4], wl[0]); csr = csound(P, wr[4], wr[0]); }
+  }
+  if (SOLVER == GX_SOLVER_HLL) return riemann_hll<false>(P, wl, wr, ff, I, csl, csr);
+  if (SOLVER == GX_SOLVER_HLLE) return riemann_hll<true>(P, wl, wr, ff, I, csl, csr);
+  if (SOLVER == GX_SOLVER_HLLC) return riemann_hllc(P, wl, wr, ff, I, csl, csr);
+#if defined(GX_FLAVOUR_FAST)
+  return 1;
+#else
+  return riemann_hlld_ref(P, wl, wr, ff, I, csl, csr);
+#endif
 }
 
 }  // namespace gxp

@@ -9,19 +9,25 @@
 // cell-centred electric field) once.
 //
 // Structure (2.5-D marching, FP64 stencil):
-//   * a CTA owns a TX x TY = 32 x 7 column of cells (8 warps, one CTA per SM: 296 CTAs = 2 per SM at 256^3) and
-//     marches along z through KZ planes;
+//   * a CTA owns a TX x TY = 32 x 11 column of cells (12 warps = 3 per scheduler, one CTA per SM at <= 168
+//     registers) and marches along z through KZ planes;
 //   * conserved planes are staged into shared memory with cp.async (LDGSTS, 8-byte
 //     elements: tile rows start on odd 8-byte offsets once the halo is included) one
 //     plane ahead of the compute, converted in place to primitives, and kept in a ring
-//     of 2*ORDER planes (the z stencil) + 1 in flight;
+//     of 2*ORDER planes (the z stencil) + 1 in flight.  The first-order stage also keeps the
+//     per-cell signal speeds of the Riemann solver in the ring (cell_speeds): there the states of
+//     a face ARE cell states, so the speeds are evaluated once per cell and direction, not per face and side;
 //   * warp r (< TY) owns row r of the tile, lane l owns cell i0+l.  Each thread solves the
-//     LOWER x face, the LOWER y face of its cell and then the UPPER z face (whose flux is
-//     carried in registers to the next plane), so every interface is solved exactly once
-//     inside the tile; warp TY solves the tile's closing faces (the y faces above the
-//     last row, then the x faces right of the last column);
-//   * face fluxes are exchanged through shared memory and the update is written with
-//     fully coalesced 256-byte row segments.
+//     LOWER x face, the LOWER y face of its cell and then the UPPER z face, so every interface is
+//     solved exactly once inside the tile; warp TY solves the tile's closing faces (the x faces
+//     right of the last column, then the y faces above the last row);
+//   * the three solves of a thread run through ONE copy of the Riemann solver in the instruction stream
+//     (a run-time loop over the face direction); what differs per direction — where the 2*ORDER states
+//     come from and where the flux goes — is compile-time specialised code either side of it (rotation of
+//     the components, swapy/swapz of src/hydro_core.f90:485-534, as constant offsets);
+//   * x and y face fluxes are exchanged through shared memory behind split mbarrier arrive/wait pairs;
+//     the z flux never leaves registers: the update of the cell is the epilogue of its z solve.  The
+//     update is written with fully coalesced 256-byte row segments.
 // Compiled per (flavour, solver): -DGX_FLAVOUR_STRICT|-DGX_FLAVOUR_FAST, -DGX_STAGE_SOLVER=n.
 #define GX_SOLVE_MASK 0xffffffffu   // every interface solve of this kernel is executed by all 32 lanes of a warp
 #include "gx_kernels.cuh"
@@ -36,11 +42,11 @@
 #ifndef GX_STAGE_SOLVER
 #error "define GX_STAGE_SOLVER (1..4)"
 #endif
-#ifndef GX_STAGE2_MINBLOCKS
-#define GX_STAGE2_MINBLOCKS 1
+#ifndef GX_STAGE_PRESPEED            // 1: per-cell signal speeds in the ring of the first-order stage
+#define GX_STAGE_PRESPEED 1
 #endif
-#ifndef GX_STAGE1_MINBLOCKS
-#define GX_STAGE1_MINBLOCKS 1
+#ifndef GX_STAGE_UB_EARLY            // 1: the base state of the update is loaded before the z solve (more registers live across it)
+#define GX_STAGE_UB_EARLY 0
 #endif
 
 namespace gx {
@@ -52,45 +58,49 @@ template <int D> __device__ __forceinline__ constexpr int rot(int c) {
   return (c == 1) ? 1 + D : (c == 1 + D) ? 1 : (c == 5) ? 5 + D : (c == 5 + D) ? 5 : c;
 }
 
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async8(unsigned smem_dst, const double* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const double* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // Split CTA barriers on mbarriers (arrive early, wait late): with one CTA per SM a full
 // __syncthreads idles the SM, so every hand-over in the plane loop is an arrive followed,
 // as late as the data dependence allows, by a parity wait.  All NT threads arrive once per
-// plane on each barrier; phase parity = plane counter & 1.
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+// plane on each barrier; phase parity = plane counter & 1.  Barriers are addressed by their
+// 32-bit shared-window address, computed once.
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
+__device__ __forceinline__ void mbar_wait(unsigned bar, int parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "MBAR_WAIT_%=:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@!p bra MBAR_WAIT_%=;\n\t}"
-      ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+      ::"r"(bar), "r"(parity) : "memory");
 }
 
-template <int NQ_, int ORDER_>
+template <int NQ_, int ORDER_, int NCF_>
 struct StageGeom {
-  static constexpr int NQ = NQ_, H = ORDER_;
+  static constexpr int NQ = NQ_, H = ORDER_, NCF = NCF_;
+  static constexpr int NV = NQ + NCF;            // staged per cell: primitives (+ signal speeds, first-order stage)
   static constexpr int TX = GX_STAGE_TX, TY = GX_STAGE_TY;
   static constexpr int NW = TY + 1, NT = NW * 32;
   static constexpr int CX = TX + 2 * H;          // staged columns  i0-H .. i0+TX+H-1
   static constexpr int RY = TY + 2 * H;          // staged rows     j0-H .. j0+TY+H-1
   static constexpr int NSLOT = 2 * H + 1;        // z ring: 2H planes of stencil + 1 in flight
   static constexpr int PCELLS = CX * RY;
-  static constexpr int PLANE = NQ * PCELLS;      // doubles per ring slot
-  static constexpr int XB = NQ * TY * (TX + 1);  // x-face flux exchange
-  static constexpr int YB = NQ * (TY + 1) * TX;  // y-face flux exchange
-  static constexpr int ZB = NQ * TY * TX;        // z-face flux hand-over (thread-private slots)
-  static constexpr size_t SMEM = sizeof(double) * ((size_t)NSLOT * PLANE + XB + YB + ZB);
+  static constexpr int PLANE = NV * PCELLS;      // doubles per ring slot
+  static constexpr int XBV = TY * (TX + 1);      // x-face flux exchange, per variable
+  static constexpr int YBV = (TY + 1) * TX;      // y-face flux exchange, per variable
+  static constexpr int XB = NQ * XBV, YB = NQ * YBV;
+  static constexpr int SCR = 32;                 // scratch: block reduction, dead-lane stores
+  static constexpr size_t SMEM = sizeof(double) * ((size_t)NSLOT * PLANE + XB + YB + SCR);
 };
 
 // block-wide min of positive doubles -> one atomicMin on the ordered bit pattern
@@ -108,81 +118,69 @@ __device__ __forceinline__ void stage_block_min(double v, unsigned long long* ds
   }
 }
 
-// One interface with a RUN-TIME sweep direction: the 2*ORDER states are gathered from the
-// staged primitive planes through per-direction variable offsets (swapy/swapz,
-// src/hydro_core.f90:485-534, as an index map), reconstructed (src/hydro_core.f90:712-798),
-// solved (prim2fhll*) and the flux is scattered back through the same map.  Keeping the
-// direction a run-time value means ONE copy of the solver in the instruction stream for
-// all x, y and z faces (the kernel is instruction-cache bound otherwise).
-//   o_m2..o_p1 : offsets (doubles, inside the ring) of variable 0 of cells  l-1, l | r, r+1
-//   vn,vt1,vt2 : offsets of the normal / transverse velocity components (bn.. = vn.. + 4 planes)
-struct FaceJob {
-  int o_m2, o_m1, o_p0, o_p1;      // ring offsets of the four cells
-  int vn, vt1, vt2;                // rotated velocity components, in doubles (component * PCELLS)
-  int out, ovs;                    // exchange-buffer offset of variable 0, variable stride
-  int on, ot1, ot2;                // rotated components of the output (component index)
-  bool store, check;
-};
-
-template <int SOLVER, int LIM, int ORDER, int NQ, int PC>
-__device__ __forceinline__ int solve_job(const gxp::Phys& P, const double* ring, double* xch, const FaceJob& J,
-                                         unsigned long long* bar_free, int free_parity) {
-  double wl[8], wr[8], fr[8];
-  {
-    const int off[8] = {0, J.vn, J.vt1, J.vt2, 4 * PC, J.vn + 4 * PC, J.vt1 + 4 * PC, J.vt2 + 4 * PC};
+// The 2*ORDER states of one interface of sweep direction D, gathered from the staged primitive planes and reconstructed
+// (limiter, src/hydro_core.f90:712-798).  p_m2 .. p_p1 point at variable 0 of cells l-1, l | r, r+1; rotated slot q
+// is storage component rot<D>(q): constant offsets.  PRE: the signal speeds of the two states come from the ring.
+template <int D, int LIM, int ORDER, int NQ, int PC, bool PRE>
+__device__ __forceinline__ void gather(const double* p_m2, const double* p_m1, const double* p_p0, const double* p_p1,
+                                       double (&wl)[8], double (&wr)[8], double& csl, double& csr) {
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      double pl = ring[J.o_m1 + off[q]], pr = ring[J.o_p0 + off[q]];
-      if (ORDER == 2) gxp::reconstruct<LIM>(ring[J.o_m2 + off[q]], pl, pr, ring[J.o_p1 + off[q]]);
-      wl[q] = pl; wr[q] = pr;
-    }
+  for (int q = 0; q < NQ; ++q) {
+    const int c = rot<D>(q) * PC;
+    double pl = p_m1[c], pr = p_p0[c];
+    if (ORDER == 2) gxp::reconstruct<LIM>(p_m2[c], pl, pr, p_p1[c]);
+    wl[q] = pl; wr[q] = pr;
   }
-  gxp::PasInfo I;
-  const int err = gxp::riemann<SOLVER>(P, wl, wr, fr, I);
-  if (free_parity >= 0) mbar_wait(bar_free, free_parity);   // every warp has finished reading the previous plane's fluxes
-  {   // lanes of the closing warp that own no face write to a scratch word instead of branching around the stores
-    __shared__ double s_dummy[32];
-    double* o = J.store ? xch + J.out : s_dummy + (threadIdx.x & 31);
-    const int ovs = J.store ? J.ovs : 0;
-    const int oc[8] = {0, J.on, J.ot1, J.ot2, 4, J.on + 4, J.ot1 + 4, J.ot2 + 4};
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) o[oc[q] * ovs] = fr[q];
+  if (PRE) {
+    const int c = (NQ + (NQ == 8 ? D : 0)) * PC;   // MHD: one fast speed per direction; hydro: the sound speed
+    csl = p_m1[c]; csr = p_p0[c];
   }
-  return J.check ? err : 0;
 }
 
+struct StageDt { double dtdx, dtdy, dtdz; };
+
 template <int SOLVER, int LIM, int ORDER, bool FLUXCD>
-__global__ void __launch_bounds__(StageGeom<(SOLVER == GX_SOLVER_HLLE || SOLVER == GX_SOLVER_HLLD) ? 8 : 5, ORDER>::NT, (ORDER == 1 ? GX_STAGE1_MINBLOCKS : GX_STAGE2_MINBLOCKS))
-k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const double* Ub, double* dst,
+struct StageTraits {
+  static constexpr bool MHD = (SOLVER == GX_SOLVER_HLLE || SOLVER == GX_SOLVER_HLLD);
+  static constexpr int NQ = MHD ? 8 : 5;
+  static constexpr int NCF = (ORDER == 1 && GX_STAGE_PRESPEED) ? (MHD ? 3 : 1) : 0;
+  using G = StageGeom<NQ, ORDER, NCF>;
+};
+
+template <int SOLVER, int LIM, int ORDER, bool FLUXCD>
+__global__ void __launch_bounds__((StageTraits<SOLVER, LIM, ORDER, FLUXCD>::G::NT), 1)
+k_stage(const StepArgs A, const StageDt sdt, const double* __restrict__ S, const double* Ub, double* dst,
         double* __restrict__ E, const int kz, unsigned long long* dtmin_bits, const int want_cfl, int* errflag) {
-  constexpr bool MHD = (SOLVER == GX_SOLVER_HLLE || SOLVER == GX_SOLVER_HLLD);
-  constexpr int NQ = MHD ? 8 : 5;
-  using G = StageGeom<NQ, ORDER>;
+  using T = StageTraits<SOLVER, LIM, ORDER, FLUXCD>;
+  using G = typename T::G;
+  constexpr bool MHD = T::MHD;
+  constexpr int NQ = T::NQ, NCF = T::NCF, NV = G::NV;
+  constexpr bool PRE = NCF > 0;
   constexpr int H = G::H, TX = G::TX, TY = G::TY, CX = G::CX, NSLOT = G::NSLOT, NT = G::NT;
   constexpr int PC = G::PCELLS;
-  constexpr int XBV = TY * (TX + 1), YBV = (TY + 1) * TX, ZBV = TY * TX;
+  constexpr int XBV = G::XBV, YBV = G::YBV;
   extern __shared__ double sm[];
   double* const ring = sm;
-  double* const xch = sm + (size_t)NSLOT * G::PLANE;     // exchange buffers: x | y | z
-  constexpr int XB0 = 0, YB0 = G::XB, ZB0 = G::XB + G::YB;
-  const double* const xb = xch + XB0;                    // [q][TY][TX+1]
-  const double* const yb = xch + YB0;                    // [q][TY+1][TX]
-  const double* const zb = xch + ZB0;                    // [q][TY][TX]
+  double* const xb = sm + (size_t)NSLOT * G::PLANE;      // [q][TY][TX+1]
+  double* const yb = xb + G::XB;                         // [q][TY+1][TX]
+  double* const scr = yb + G::YB;                        // [32]
+  __shared__ unsigned long long bars[2];
 
   const Grid& g = A.g;
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int i0 = 1 + (int)blockIdx.x * TX, j0 = 1 + (int)blockIdx.y * TY, k0 = A.kbeg + (int)blockIdx.z * kz;
   const int kend = min(k0 + kz - 1, A.klast);
   const long long vs = g.vs;
+  const bool main_warp = wrp < TY;                       // warp-uniform
 
   // ---- plane staging: conserved -> shared (cp.async), converted in place to primitives ----
   // Ownership: a main-warp thread stages and converts ITS OWN centre cell (so its z solves, which
   // only read its own column, never wait for another thread), and the halo frame of the plane
-  // (consumed ORDER+1 planes later by the x/y solves) is dealt round-robin.
-  // warp-uniform by construction; in the first-order kernel telling the compiler so (a vote) pays, in the second-order one it does not
-  const bool main_warp = (ORDER == 1) ? (bool)__all_sync(0xffffffffu, wrp < TY) : (wrp < TY);
+  // (consumed ORDER+1 planes later by the x/y solves) is dealt one cell per thread from the LAST thread
+  // down, so the closing warp (two solves per plane instead of three) takes its share first.
   const int cidx = (min(wrp, TY - 1) + H) * CX + (lane + H);   // this thread's cell inside a staged plane
   constexpr int HC = PC - TY * TX;                       // halo cells of a staged plane
+  static_assert(HC <= NT, "one halo cell per thread");
   auto halo_cell = [&](int h) {                          // h-th halo cell -> plane-local index
     if (h < H * CX) return h;                                                   // rows below the tile
     if (h < H * CX + 2 * H * TY) {
@@ -191,13 +189,11 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
     }
     return h - (H * CX + 2 * H * TY) + (H + TY) * CX;                           // rows above the tile
   };
+  const bool has_halo = (NT - 1 - tid) < HC;
+  const int hcell = halo_cell(has_halo ? NT - 1 - tid : 0);
   auto slot_off = [&](int p) { return ((p - (k0 - H)) % NSLOT) * G::PLANE; };
-  // Every thread stages (and later converts) at most two cells of a plane: its own centre cell and one cell of
-  // the halo frame.  Their plane-local indices and their (i, j) offsets inside a global plane — clamped to the
-  // array, wrapped where the block is its own periodic neighbour — are fixed for the whole march: compute them once.
-  static_assert(HC <= NT, "one halo cell per thread");
-  const bool has_halo = tid < HC;
-  const int hcell = halo_cell(has_halo ? tid : 0);
+  // The (i, j) offsets of a thread's two cells inside a global plane — clamped to the array, wrapped where the
+  // block is its own periodic neighbour — are fixed for the whole march.
   auto ij_off = [&](int c) {
     const int rr = c / CX, cc = c - rr * CX;
     int i = min(i0 - H + cc, g.nx + 2), j = min(j0 - H + rr, g.ny + 2);
@@ -207,12 +203,14 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
   };
   const int own_off = ij_off(cidx), halo_off = ij_off(hcell);
   const long long gplane = (long long)g.px * g.py;
-  auto stage_cell = [&](double* sl, int c, const double* src) {
+  const unsigned ring_u32 = smem_u32(ring);
+  auto stage_cell = [&](int slot, int c, const double* src) {
+    const unsigned d = ring_u32 + (unsigned)(slot + c) * 8u;
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) cp_async8(sl + q * PC + c, src + q * vs);
+    for (int q = 0; q < NQ; ++q) cp_async8(d + (unsigned)(q * PC) * 8u, src + q * vs);
   };
   auto issue_load = [&](int p) {
-    double* sl = ring + slot_off(p);
+    const int sl = slot_off(p);
     int kk = min(p, g.nz + 2);
     if (A.wrap[2]) kk = kk < 1 ? kk + g.nz : (kk > g.nz ? kk - g.nz : kk);
     const double* pl = S + (long long)(kk + 1) * gplane;
@@ -221,12 +219,18 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
     cp_async_commit();
   };
   auto convert_cell = [&](double* sl, int c) {
-    double u[8], w[8], T;
+    double u[8], w[8], Tk;
 #pragma unroll
     for (int q = 0; q < NQ; ++q) u[q] = sl[q * PC + c];
-    gxp::u2prim<MHD, false, true>(A.phys, u, w, 0.0, T);
+    gxp::u2prim<MHD, false, true>(A.phys, u, w, 0.0, Tk);
 #pragma unroll
     for (int q = 0; q < NQ; ++q) sl[q * PC + c] = w[q];
+    if (PRE) {
+      double cs[3];
+      gxp::cell_speeds<MHD>(A.phys, w, cs);
+#pragma unroll
+      for (int d = 0; d < NCF; ++d) sl[(NQ + d) * PC + c] = cs[d];
+    }
   };
   auto convert = [&](int p) {      // each thread converts exactly the cells it staged itself
     double* sl = ring + slot_off(p);
@@ -235,12 +239,10 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
   };
 
   // Barriers of the plane loop (all NT threads arrive once per plane on each):
-  //   bars[0] XY   : x and y face fluxes of this plane are in the exchange buffers
-  //   bars[1] FREE : this thread has consumed the exchange buffers (they may be overwritten)
-  // The z flux is handed over in thread-private slots and the newest plane's centre cell is
-  // converted by its consumer, so neither needs a CTA-wide barrier.
-  __shared__ unsigned long long bars[2];
-  if (tid == 0) { mbar_init(&bars[0], NT); mbar_init(&bars[1], NT); }
+  //   XY   : x and y face fluxes of this plane are in the exchange buffers
+  //   FREE : this thread has consumed the exchange buffers (they may be overwritten)
+  const unsigned bar_xy = smem_u32(&bars[0]), bar_free = smem_u32(&bars[1]);
+  if (tid == 0) { mbar_init(bar_xy, NT); mbar_init(bar_free, NT); }
 #pragma unroll 1
   for (int p = k0 - H; p <= k0 + H - 1; ++p) issue_load(p);
   cp_async_wait_all();
@@ -250,125 +252,159 @@ k_stage(const StepArgs A, const double dt, const double* __restrict__ S, const d
 
   const int i = i0 + lane, j = j0 + wrp;
   const bool cell_ok = main_warp && i <= g.nx && j <= g.ny;
-  const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
-  // plane-invariant parts of this thread's three face jobs (x: extra warp closes right of the last column, row = lane;
-  // y: extra warp closes the row above the tile)
+  // plane-invariant parts of this thread's face jobs (x: the extra warp closes right of the last column, row = lane;
+  // y: the extra warp closes the row above the tile)
   const int row_x = main_warp ? wrp : min(lane, TY - 1), col_x = main_warp ? lane : TX;
-  const int cx_const = (row_x + H) * CX + (col_x + H), cy_const = cidx + (main_warp ? 0 : CX);
-  const int out_x = XB0 + row_x * (TX + 1) + col_x;
-  const bool store_x = main_warp || lane < TY;
+  const int c0x = (row_x + H) * CX + (col_x + H);        // right cell of my x face
+  const int c0y = cidx + (main_warp ? 0 : CX);           // upper cell of my y face
+  // lanes of the closing warp that own no x face write to a scratch word instead of branching around the stores
+  double* const out_x = (main_warp || lane < TY) ? xb + row_x * (TX + 1) + col_x : scr + lane;
+  const int ovs_x = (main_warp || lane < TY) ? XBV : 0;
+  double* const out_y = yb + wrp * TX + lane;
   const bool check_x = main_warp ? (i <= g.nx + 1 && j <= g.ny) : (lane < TY && i0 + TX <= g.nx + 1 && j0 + lane <= g.ny);
   const bool check_y = (i <= g.nx && j <= g.ny + 1);
+  const int njobs = main_warp ? 3 : 2;
+  // hprev: flux through the lower z face of my cell (the previous plane's z solve), storage components
   double hprev[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) hprev[q] = 0.0;
   double dtp = 1.e30;
   int err = 0;
-  int it = 0;                                             // plane counter (barrier phase)
+  int it = 0;                                             // x/y plane counter (barrier phase)
 
-  for (int k = k0 - 1; k <= kend; ++k, ++it) {
+#pragma unroll 1
+  for (int k = k0 - 1; k <= kend; ++k) {
     if (k < kend) issue_load(k + H + 1);                  // into the slot of plane k-H: its last readers were this thread's
                                                           // own z solve (centre) and x/y solves >= 1 XY barrier ago (halo)
-    const int sk = slot_off(k);
-    const bool xy = k >= k0;
-    // jobs of this thread: main warps solve the lower y face, the lower x face and the upper z face
-    // of their cell; warp TY closes the tile (y faces above the last row, x faces right of the last column)
-    const int njobs = main_warp ? 3 : 2;
-    const int sp1 = slot_off(k + 1), sm1 = (ORDER == 2) ? slot_off(k - 1) : sk, sp2 = (ORDER == 2) ? slot_off(k + 2) : sp1;
-    double ub[8];
+    const bool xy = k >= k0;                              // the chunk's leading plane only supplies the first z flux
+    const double* const pk = ring + slot_off(k);
     const long long cg = g.idx(min(i, g.nx), min(j, g.ny), max(k, 1));
+#if !GX_STAGE_UB_EARLY
+    if (xy && cell_ok && Ub != S) {                       // second stage: the base state is not the staged array; start it towards L2
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) if (!(FLUXCD && q >= 5)) prefetch_l2(Ub + q * vs + cg);
+    }
+#endif
+    // jobs of this thread: x face (0), y face (1), upper z face (2; main warps only)
 #pragma unroll 1
-    for (int jb = (xy ? 0 : 2); jb < njobs; ++jb) {
-      // branch-free job descriptor: the job type only steers selects (no divergent if/else chain per solve)
-      FaceJob J;
-      const int jt = jb == 0 ? 1 : (jb == 1 ? 0 : 2);     // job order: x face, y face, z face
-      const bool isx = jt == 1, isz = jt == 2;
-      const int cxy = isx ? sk + cx_const : sk + cy_const;
-      const int st = isx ? 1 : CX;
-      J.o_p0 = isz ? sp1 + cidx : cxy;
-      J.o_m1 = isz ? sk + cidx : cxy - st;
-      J.o_m2 = isz ? ((ORDER == 2) ? sm1 + cidx : sk + cidx) : cxy - 2 * st;
-      J.o_p1 = isz ? ((ORDER == 2) ? sp2 + cidx : sp1 + cidx) : cxy + st;
-      J.on = isx ? 1 : (isz ? 3 : 2); J.ot1 = isx ? 2 : (isz ? 2 : 1); J.ot2 = isz ? 1 : 3;
-      J.out = isx ? out_x : (isz ? ZB0 : YB0) + wrp * TX + lane;
-      J.ovs = isx ? XBV : (isz ? ZBV : YBV);
-      J.store = isx ? store_x : true;
-      J.check = isx ? check_x : (isz ? cell_ok : check_y);
-      if (isz && xy) {                                    // base state for the update: in flight during the z solve
+    for (int jt = (xy ? 0 : 2); jt < njobs; ++jt) {
+      double wl[8], wr[8], fr[8], csl = 0.0, csr = 0.0;
+      if (jt == 0) {
+        const double* c = pk + c0x;
+        gather<0, LIM, ORDER, NQ, PC, PRE>(c - 2, c - 1, c, c + 1, wl, wr, csl, csr);
+      } else if (jt == 1) {
+        const double* c = pk + c0y;
+        gather<1, LIM, ORDER, NQ, PC, PRE>(c - 2 * CX, c - CX, c, c + CX, wl, wr, csl, csr);
+      } else {
+        const double* cm = (ORDER == 2) ? ring + slot_off(k - 1) + cidx : pk + cidx;
+        const double* cp1 = ring + slot_off(k + 1) + cidx;
+        const double* cp2 = (ORDER == 2) ? ring + slot_off(k + 2) + cidx : cp1;
+        gather<2, LIM, ORDER, NQ, PC, PRE>(cm, pk + cidx, cp1, cp2, wl, wr, csl, csr);
+      }
+#if GX_STAGE_UB_EARLY
+      double ub[8];
+      if (jt == 2 && xy) {                                // base state for the update: in flight during the z solve
 #pragma unroll
         for (int q = 0; q < NQ; ++q) if (!(FLUXCD && q >= 5)) ub[q] = Ub[q * vs + cg];
       }
-      J.vn = J.on * PC; J.vt1 = J.ot1 * PC; J.vt2 = J.ot2 * PC;
-      // the first x/y store of a plane waits until every thread has consumed the previous plane's fluxes
-      err |= solve_job<SOLVER, LIM, ORDER, NQ, PC>(A.phys, ring, xch, J, &bars[1], (jb == 0 && it > 0) ? ((it - 1) & 1) : -1);
-      if (jb == 1) mbar_arrive(&bars[0]);                 // my x and y fluxes are written
-    }
-    if (!xy) mbar_arrive(&bars[0]);                       // (no x/y faces on the chunk's leading plane)
-    double h[8];
-    if (main_warp) {
+#endif
+      gxp::PasInfo I;
+      const int e = gxp::riemann<SOLVER, PRE>(A.phys, wl, wr, fr, I, csl, csr);
+      if (jt == 0) {
+        err |= check_x ? e : 0;
+        if (it > 0) mbar_wait(bar_free, (it - 1) & 1);    // every thread has finished reading the previous plane's fluxes
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) h[q] = zb[q * ZBV + wrp * TX + lane];
-    }
-    mbar_wait(&bars[0], it & 1);                          // all x/y face fluxes of this plane visible
-    if (xy && cell_ok) {
-      const long long c = g.idx(i, j, k);
-      double un[8];
+        for (int q = 0; q < NQ; ++q) out_x[rot<0>(q) * ovs_x] = fr[q];
+      } else if (jt == 1) {
+        err |= check_y ? e : 0;
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        if (FLUXCD && q >= 5) continue;                   // B is advanced from E by k_bupdate
-        const double flo = xb[q * XBV + wrp * (TX + 1) + lane], fup = xb[q * XBV + wrp * (TX + 1) + lane + 1];
-        const double glo = yb[q * YBV + wrp * TX + lane], gup = yb[q * YBV + (wrp + 1) * TX + lane];
-        // step(): up = u - dt/dx (f(i)-f(i-1)) - dt/dy (g(j)-g(j-1)) - dt/dz (h(k)-h(k-1))   hydro_solver.f90:105-107
-        const double v = ub[q] - dtdx * (fup - flo) - dtdy * (gup - glo) - dtdz * (h[q] - hprev[q]);
-        un[q] = v;
-        dst[q * vs + c] = v;
-      }
-      if (FLUXCD) {                                       // get_efield, flux_cd_module.f90:258-265
-        const double f6l = xb[6 * XBV + wrp * (TX + 1) + lane], f6u = xb[6 * XBV + wrp * (TX + 1) + lane + 1];
-        const double f7l = xb[7 * XBV + wrp * (TX + 1) + lane], f7u = xb[7 * XBV + wrp * (TX + 1) + lane + 1];
-        const double g5l = yb[5 * YBV + wrp * TX + lane], g5u = yb[5 * YBV + (wrp + 1) * TX + lane];
-        const double g7l = yb[7 * YBV + wrp * TX + lane], g7u = yb[7 * YBV + (wrp + 1) * TX + lane];
-        E[0 * vs + c] = 0.25 * (-g7l - g7u + hprev[6] + h[6]);
-        E[1 * vs + c] = 0.25 * (+f7l + f7u - hprev[5] - h[5]);
-        E[2 * vs + c] = 0.25 * (-f6l - f6u + g5l + g5u);
-      } else if (want_cfl) {                              // get_timestep candidates of the new state, hydro_core.f90:644-675
-        double w[8], T;
-        gxp::u2prim<MHD, false, true>(A.phys, un, w, 0.0, T);
-        if (MHD) {
-          double cx, cy, cz;
-          gxp::cfast3(A.phys, w[4], w[0], w[5], w[6], w[7], cx, cy, cz);
-          dtp = fmin(dtp, g.dx / (fabs(w[1]) + cx));
-          dtp = fmin(dtp, g.dy / (fabs(w[2]) + cy));
-          dtp = fmin(dtp, g.dz / (fabs(w[3]) + cz));
-        } else {
-          const double cs = gxp::csound(A.phys, w[4], w[0]);
-          dtp = fmin(dtp, g.dx / (fabs(w[1]) + cs));
-          dtp = fmin(dtp, g.dy / (fabs(w[2]) + cs));
-          dtp = fmin(dtp, g.dz / (fabs(w[3]) + cs));
+        for (int q = 0; q < NQ; ++q) out_y[rot<1>(q) * YBV] = fr[q];
+        mbar_arrive(bar_xy);                              // my x and y fluxes are written
+      } else {
+        err |= cell_ok ? e : 0;
+        // ---- epilogue of the z solve: the update of my cell in plane k (fr = flux through its upper z face) ----
+        double h[8];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) h[rot<2>(q)] = fr[q];
+        if (xy) {
+#if !GX_STAGE_UB_EARLY
+          double ub[8];
+          if (cell_ok) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) if (!(FLUXCD && q >= 5)) ub[q] = Ub[q * vs + cg];
+          }
+#endif
+          mbar_wait(bar_xy, it & 1);                      // all x/y face fluxes of this plane visible
+          if (cell_ok) {
+            const long long c = g.idx(i, j, k);
+            const double* xr = xb + wrp * (TX + 1) + lane;
+            const double* yr = yb + wrp * TX + lane;
+            double un[8];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+              if (FLUXCD && q >= 5) continue;             // B is advanced from E by k_bupdate
+              const double flo = xr[q * XBV], fup = xr[q * XBV + 1];
+              const double glo = yr[q * YBV], gup = yr[q * YBV + TX];
+              // step(): up = u - dt/dx (f(i)-f(i-1)) - dt/dy (g(j)-g(j-1)) - dt/dz (h(k)-h(k-1))   hydro_solver.f90:105-107
+              const double v = ub[q] - sdt.dtdx * (fup - flo) - sdt.dtdy * (gup - glo) - sdt.dtdz * (h[q] - hprev[q]);
+              un[q] = v;
+              dst[q * vs + c] = v;
+            }
+            if (FLUXCD) {                                 // get_efield, flux_cd_module.f90:258-265
+              const double f6l = xr[6 * XBV], f6u = xr[6 * XBV + 1];
+              const double f7l = xr[7 * XBV], f7u = xr[7 * XBV + 1];
+              const double g5l = yr[5 * YBV], g5u = yr[5 * YBV + TX];
+              const double g7l = yr[7 * YBV], g7u = yr[7 * YBV + TX];
+              E[0 * vs + c] = 0.25 * (-g7l - g7u + hprev[6] + h[6]);
+              E[1 * vs + c] = 0.25 * (+f7l + f7u - hprev[5] - h[5]);
+              E[2 * vs + c] = 0.25 * (-f6l - f6u + g5l + g5u);
+            } else if (want_cfl) {                        // get_timestep candidates of the new state, hydro_core.f90:644-675
+              double w[8], Tk;
+              gxp::u2prim<MHD, false, true>(A.phys, un, w, 0.0, Tk);
+              if (MHD) {
+                double cx, cy, cz;
+                gxp::cfast3(A.phys, w[4], w[0], w[5], w[6], w[7], cx, cy, cz);
+                dtp = fmin(dtp, g.dx / (fabs(w[1]) + cx));
+                dtp = fmin(dtp, g.dy / (fabs(w[2]) + cy));
+                dtp = fmin(dtp, g.dz / (fabs(w[3]) + cz));
+              } else {
+                const double cs = gxp::csound(A.phys, w[4], w[0]);
+                dtp = fmin(dtp, g.dx / (fabs(w[1]) + cs));
+                dtp = fmin(dtp, g.dy / (fabs(w[2]) + cs));
+                dtp = fmin(dtp, g.dz / (fabs(w[3]) + cs));
+              }
+            }
+          }
+          mbar_arrive(bar_free);                          // done reading the exchange buffers
         }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) hprev[q] = h[q];
       }
     }
-    mbar_arrive(&bars[1]);                                // done reading the exchange buffers
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) hprev[q] = h[q];
+    if (!main_warp && xy) {                               // the closing warp reads no fluxes; it keeps in step with the planes
+      mbar_wait(bar_xy, it & 1);
+      mbar_arrive(bar_free);
+    }
+    if (xy) ++it;
     if (k < kend) { cp_async_wait_all(); convert(k + H + 1); }   // next plane -> primitives (own cells)
   }
   __syncthreads();
   if (err) atomicOr(errflag, 1);
-  if (!FLUXCD && want_cfl) stage_block_min<NT>(dtp, dtmin_bits, xch);
+  if (!FLUXCD && want_cfl) stage_block_min<NT>(dtp, dtmin_bits, scr);
 }
 
 // ---------------------------------------------------------------------------
 template <int SOLVER, int LIM, int ORDER, bool FLUXCD>
 static int launch_one(const StepArgs& A, double dt, const double* S, const double* Ub, double* dst, double* E, int kz,
                       unsigned long long* dtmin_bits, int want_cfl, int* errflag, cudaStream_t st) {
-  constexpr bool MHD = (SOLVER == GX_SOLVER_HLLE || SOLVER == GX_SOLVER_HLLD);
-  using G = StageGeom<MHD ? 8 : 5, ORDER>;
+  using G = typename StageTraits<SOLVER, LIM, ORDER, FLUXCD>::G;
+  static_assert(G::SMEM <= 227 * 1024, "stage kernel tile does not fit the shared memory of one SM");
   auto kern = k_stage<SOLVER, LIM, ORDER, FLUXCD>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM) != cudaSuccess) return GX_ECUDA;
   const Grid& g = A.g;
+  const StageDt sdt = {dt / g.dx, dt / g.dy, dt / g.dz};
   dim3 grid((g.nx + G::TX - 1) / G::TX, (g.ny + G::TY - 1) / G::TY, (A.klast - A.kbeg + 1 + kz - 1) / kz);
-  kern<<<grid, G::NT, G::SMEM, st>>>(A, dt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag);
+  kern<<<grid, G::NT, G::SMEM, st>>>(A, sdt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag);
   return GX_OK;
 }
 
