@@ -120,43 +120,62 @@ def workload(n: int, world: int, strong: bool = False, solver: str = "hlld") -> 
     return p
 
 
-def cpu_reference(p_block: Params, steps: int, warmup: int, threads: int):
-    """The reference's CPU path (C++ restatement, oracle/, -O3 -ffp-contract=off) on a bounded
-    sample of the workload: a z-slab of the same initial conditions (OT is z-invariant, so the
-    per-zone work is identical), one block per thread like the reference's MPI ranks."""
+CPU_RATE_GUESS = 1.2e7      # zone-updates/s of the oracle on ~16 host threads (sizes the bounded sample; the measured rate is what is reported)
+
+
+def cpu_reference(p_block: Params, steps: int, warmup: int, threads: int, budget_s: float = 90.0):
+    """The reference's CPU path (C++ restatement, oracle/, -O3 -ffp-contract=off): one block per host thread, split along x
+    like the reference's MPI ranks.  The whole grid when `steps + warmup` steps of it fit the time budget, otherwise a bounded
+    sample: a z-slab of the same initial conditions (OT is z-invariant, so the per-zone work is identical)."""
     from tests.oracle_lib import Oracle
-    nzs = 16
-    # one block per host thread, split along x like the reference's MPI ranks: the largest block count that
-    # divides the grid and leaves every block at least 4 cells wide (the host's core count need not divide 256)
+    # the largest block count that divides the grid and leaves every block at least 4 cells wide (the host's core count need not divide 256)
     threads = max(t for t in range(1, max(1, threads) + 1) if p_block.nxtot % t == 0 and p_block.nxtot // t >= 4)
+    plane = p_block.nxtot * p_block.nytot
+    nzs = int(budget_s * CPU_RATE_GUESS * (threads / 16.0) / (plane * max(1, steps + warmup)))
+    nzs = max(4, min(p_block.nztot, nzs))
+    if nzs < p_block.nztot:
+        nzs = max(4, nzs // 4 * 4)
+    full = nzs == p_block.nztot
     p = p_block.replace(nztot=nzs, zmax=p_block.zmax * nzs / p_block.nztot, MPI_NBX=threads, MPI_NBY=1, MPI_NBZ=1)
     o = Oracle(p, fast=True, threads=threads)
     g = problems.orszag_tang(p.replace(MPI_NBX=1), (0, 0, 0))
     o.scatter_u(g)
+    del g
     o.start()
     o.iter = 11                                   # past the 10-step CFL ramp (hydro_core.f90:677-682)
-    o.run_timed(max(1, warmup))
+    if warmup > 0:
+        o.run_timed(warmup)
     sec = o.run_timed(steps)
     zones = p.nxtot * p.nytot * p.nztot
-    sample = f"{p.nxtot}x{p.nytot}x{nzs} slab of the same OT field, {threads} blocks x 1 thread (x-split like the reference's MPI), {steps} steps after {max(1, warmup)} warm-up"
-    return zones * steps / sec, sec / steps * 1e3, sample, threads
+    what = "the whole grid" if full else f"{p.nxtot}x{p.nytot}x{nzs} slab of the same OT field (bounded sample)"
+    sample = f"{what}, {threads} blocks x 1 thread (x-split like the reference's MPI), {steps} steps after {warmup} warm-up"
+    return zones * steps / sec, sec / steps * 1e3, sample, threads, full
+
+
+def workload_name(n: int, strong: bool, solver: str, flux_cd: bool) -> str:
+    return ((f"3-D Orszag-Tang {n}^3 in total (BASELINE configs[2], strong scaling)" if strong else f"3-D Orszag-Tang {n}^3 per GPU (BASELINE configs[1])")
+            + ", " + solver.upper() + (" + flux-CD" if flux_cd else "") + ", minmod, periodic, cfl 0.2")
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port: no Fortran compiler / MPI in this image)
+    on the host cores, same workload, metric and unit; --steps / --warmup are honoured.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    p = workload(args.n, 1)
-    steps = max(1, min(args.steps, 3))
-    v, ms, sample, threads = cpu_reference(p, steps, min(args.warmup, 1), threads)
+    p = workload(args.n, 1, False, args.solver)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    v, ms, sample, threads, full = cpu_reference(p, steps, warmup, threads)
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"3-D Orszag-Tang {args.n}^3 HLLD+flux-CD minmod periodic (CPU: bounded slab sample)", "sample": sample},
+        "config": {"workload": workload_name(args.n, False, args.solver, p.enable_flux_cd), "grid_total": [p.nxtot, p.nytot, p.nztot], "neq": p.neq,
+                   "sample": sample, "whole_grid": full},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference is Fortran+MPI and cannot be built in this image (no Fortran compiler/MPI); this is the line-faithful C++ restatement in oracle/",
+        "note": "reference is Fortran+MPI and cannot be built in this image (no Fortran compiler/MPI); this is the line-faithful C++ restatement in oracle/ "
+                "(ms_per_step is per step of the sampled grid; value is zone-updates/s and does not depend on the sample size)",
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -174,6 +193,7 @@ def main():
     ap.add_argument("--strict", action="store_true", help="use the -fmad=false bit-comparison kernels")
     ap.add_argument("--solver", default="hlld", choices=sorted(SOLVERS), help="Riemann solver (BASELINE configs[4] sweep); the headline metric is hlld")
     ap.add_argument("--strong", action="store_true", help="strong scaling: --n is the TOTAL grid side, split into z-slabs over the GPUs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the 512^3 lines (extra.grid512 at N=1; extra.weak512 / extra.strong512 at N>1)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -275,12 +295,49 @@ def main():
     res_sec = max_over_ranks(time.perf_counter() - t0)
     barrier()
 
+    # ---------------- BASELINE configs[2] / the north_star's target grid, same run: 512^3 ----------------
+    peak_gbs, peak_src = measured_peaks()
+
+    def measure_grid(n: int, strong: bool, steps: int = 5, warmup: int = 3):
+        """Device-resident zone-updates/s of an n^3 block per GPU (weak) or n^3 in total (strong), same kernels and timing rules."""
+        try:
+            if strong and n % world:
+                return {"skipped": f"{n} planes do not split over {world} GPUs"}
+            p2 = workload(n, world, strong, args.solver).replace(strict_fp=args.strict)
+            b2 = make_rank_block(p2, rank, world, local_rank, nb=nb)
+            try:
+                u2 = problems.orszag_tang(b2.p, coords)
+                b2.set_state(u2)
+                del u2
+                t2, i2, _ = b2.run(warmup, 0.0, 1)
+                barrier()
+                t2, i2, _ = b2.run(steps, t2, i2)
+                ms2 = max_over_ranks(b2.last_elapsed_ms)
+                barrier()
+                zr = b2.p.nx * b2.p.ny * b2.p.nz
+                v2 = zr * world * steps / (ms2 * 1e-3)
+                return {"value": v2, "unit": UNIT, "ms_per_step": ms2 / steps, "steps": steps, "warmup": warmup, "n_gpus": world,
+                        "scaling": "strong" if strong else "weak", "grid_total": [b2.p.nxtot, b2.p.nytot, b2.p.nztot],
+                        "whole_step_frac": 40.0 * b2.p.neq * zr * steps / (ms2 * 1e-3) / 1e9 / peak_gbs,
+                        "workload": workload_name(n, strong, args.solver, b2.p.enable_flux_cd)}
+            finally:
+                b2.close()
+        except Exception as e:      # an extra line never takes the headline down with it
+            return {"error": f"{type(e).__name__}: {e}"}
+
+    extra = {}
+    if not args.no_extras and args.n == 256 and not args.strong and args.solver == "hlld":
+        if world == 1:
+            extra["grid512"] = measure_grid(512, False)
+        else:
+            extra["weak512"] = measure_grid(512, False)
+            extra["strong512"] = measure_grid(512, True)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    peak_gbs, peak_src = measured_peaks()
     step_ms = ms / args.steps
     tot_prof = sum(v[0] for v in ktimes.values())
     fused = ktimes["stage2"][1] > 0
@@ -292,14 +349,17 @@ def main():
         dom_name, dom_key, dom_bytes_zone = f"k_stage<{args.solver.upper()},minmod,ORDER=2{',fluxCD' if pb.enable_flux_cd else ''}> (fused prim+3 sweeps+E+update)", "stage2", 8 * dom_doubles
     else:
         dom_name, dom_key, dom_bytes_zone = "k_flux<HLLD,minmod> (3 launches per stage, unfused path)", "flux", 2 * 8 * pb.neq * 3
+    # time of the dominant kernel per step = everything its class launched in a step (the overlap path of N > 1 launches a
+    # stage three times: two boundary slabs and the interior), against the bytes of the whole block
     dom_ms, dom_n = ktimes[dom_key]
-    dom_avg_ms = dom_ms / dom_n if dom_n else None
-    dom_gbs = dom_bytes_zone * zones_rank / (dom_avg_ms * 1e-3) / 1e9 if dom_avg_ms else None
+    dom_step_ms = dom_ms / nprof if dom_n else None
+    dom_launches_per_step = dom_n / nprof if nprof else None
+    dom_gbs = dom_bytes_zone * zones_rank / (dom_step_ms * 1e-3) / 1e9 if dom_step_ms else None
     traffic = None
-    try:       # DRAM bytes of that kernel per launch from the committed ncu --set full capture (same workload only)
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+    try:       # DRAM bytes of that kernel per launch from the committed ncu --set full capture: only for the captured launch geometry
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             tj = json.load(f)
-        if fused and tj.get("zones") == zones_rank and args.solver == "hlld":
+        if fused and tj.get("zones") == zones_rank and args.solver == "hlld" and world == 1 and dom_launches_per_step == 1:
             traffic = tj["stage2_dram_bytes_per_launch"]
     except Exception:
         pass
@@ -309,7 +369,7 @@ def main():
     # issue rate of this GPU (profiles/peaks_r1.json) and all instructions against the issue slots at the sampled clock
     fp64 = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             tj2 = json.load(f)
         with open(os.path.join(ROOT, "profiles", "peaks_r1.json")) as f:
             pk = json.load(f)
@@ -325,9 +385,9 @@ def main():
         pass
     roofline = {
         "bound": "hbm", "achieved": dom_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": (dom_gbs / peak_gbs if dom_gbs else None), "traffic": traffic,
-        "peak_source": peak_src, "kernel": dom_name, "avg_launch_ms": dom_avg_ms,
+        "peak_source": peak_src, "kernel": dom_name, "ms_per_step": dom_step_ms, "launches_per_step": dom_launches_per_step,
         "algorithmic_bytes_per_zone": dom_bytes_zone,
-        "definition": "algorithmic bytes of the dominant kernel (read U* 8 + U^n 5, write U^{n+1} 5 + E 3 = 21 doubles per zone with flux-CD) x zones per GPU / its average launch time (CUDA events on the solver's stream)",
+        "definition": "algorithmic bytes of the dominant kernel (read U* 8 + U^n 5, write U^{n+1} 5 + E 3 = 21 doubles per zone with flux-CD) x zones per GPU / the device time its launches take per step (CUDA events on the solver's stream)",
         "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak_gbs, "algorithmic_bytes_per_zone": bytes_zone,
                        "definition": "40*neq B per zone-update (5*neq doubles: 320 B MHD, 200 B hydro) x zones per GPU / whole-step device time"},
         "fp64_note": "the kernel is FP64-pipe/issue bound, not HBM bound: see profiles/ (sm__inst_executed_pipe_fp64 ~47%, issue ~56%, dram ~16%) and DESIGN.md",
@@ -338,14 +398,14 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:        # reported baseline: rank 0 at N = 1 only (bounded sample, a few seconds)
         threads = os.cpu_count() or 1
-        v, _ms, sample, threads = cpu_reference(workload(args.n, 1), 2, 1, threads)
+        v, _ms, sample, threads, _full = cpu_reference(workload(args.n, 1), 2, 1, threads, budget_s=12.0)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
 
     line = {
         "metric": METRIC if args.solver == "hlld" else f"{'MHD' if pb.mhd else 'hydro'} zone-updates/s ({args.solver.upper()}{' + flux-CD' if pb.enable_flux_cd else ''}, FP64)",
         "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": (f"3-D Orszag-Tang {args.n}^3 in total (BASELINE configs[2], strong scaling)" if args.strong else f"3-D Orszag-Tang {args.n}^3 per GPU (BASELINE configs[1])") + ", " + (f"{args.solver.upper()}" + (" + flux-CD" if pb.enable_flux_cd else "")) + ", minmod, periodic, cfl 0.2",
+        "config": {"workload": workload_name(args.n, args.strong, args.solver, pb.enable_flux_cd),
                    "grid_total": [pb.nxtot, pb.nytot, pb.nztot], "blocks": list(nb), "neq": pb.neq,
                    "kernels": "strict (-fmad=false)" if args.strict else "fast (-fmad=true)",
                    "l2": f"working set (u, up, E: {(2 * pb.neq + 3) * 8 * (pb.nx + 32) * (pb.ny + 4) * (pb.nz + 4) / 1e9:.1f} GB per GPU) exceeds the 126 MB L2; no flush needed",
@@ -360,6 +420,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "finite": finite, "last_dt": last_dt,
+        "extra": extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

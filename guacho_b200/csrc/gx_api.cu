@@ -80,7 +80,7 @@ struct gx_solver {
   bool have_state = false;
   bool ghosts_stale = false;   // self-periodic ghost layers of u/up not materialised since the last fused step
   bool fused = false;      // fused stage kernels (gx_stage.cu); otherwise the pass-per-routine kernels
-  int kz = 16;             // planes one CTA of the fused stage kernel marches through
+  int kz = 0;              // planes one CTA of the fused stage kernel marches through (0: the launcher fills whole waves of SMs; GX_KZ overrides)
   double time = 0.0;
   // block topology (mpi_cart_shift results; -1 = MPI_PROC_NULL)
   int nb[3] = {1, 1, 1}, co[3] = {0, 0, 0};
@@ -582,6 +582,7 @@ int gx_create(const gx_config* c, gx_solver** out) {
   g.dx = c->dx; g.dy = c->dy; g.dz = c->dz;
   s->A.phys.cv = c->cv; s->A.phys.gamma = c->gamma; s->A.phys.Tempsc = c->Tempsc; s->A.phys.inv_cv = 1.0 / c->cv; s->A.phys.m4gamma = -4.0 * c->gamma;
   s->A.phys.eos = c->eq_of_state; s->A.phys.neqdyn = c->neqdyn; s->A.phys.npas = c->npas;
+  s->A.idx3[0] = 1.0 / c->dx; s->A.idx3[1] = 1.0 / c->dy; s->A.idx3[2] = 1.0 / c->dz;
   s->A.solver = c->riemann_solver; s->A.limiter = c->slope_limiter;
   s->A.flux_cd = c->enable_flux_cd; s->A.eight_wave = c->eight_wave; s->A.user_src = c->user_source_terms;
   s->A.grav.n = 0;
@@ -607,22 +608,7 @@ int gx_create(const gx_config* c, gx_solver** out) {
   // fused stage kernels cover the dynamic variables with the adiabatic equation of state; passives, the 8-wave / user sources and
   // eta != 0 (viscous_copy needs up's stale half-step ghosts) take the pass-per-routine kernels
   s->fused = c->npas == 0 && !c->eight_wave && !c->user_source_terms && c->eta == 0.0 && c->eq_of_state == GX_EOS_ADIABATIC && !getenv("GX_NO_FUSED");
-  {
-    // planes per CTA of the fused stage kernel: as long as possible (the z prologue costs 2*ORDER
-    // plane loads and one extra z solve per chunk) while the grid still fills whole waves of SMs
-    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-    const long long tiles = (long long)((nx + GX_STAGE_TX - 1) / GX_STAGE_TX) * ((ny + GX_STAGE_TY - 1) / GX_STAGE_TY);
-    int best_kz = nz; double best_eff = -1.0;
-    for (int chunks = 1; chunks <= nz; ++chunks) {
-      const int kzc = (nz + chunks - 1) / chunks;
-      const long long total = tiles * ((nz + kzc - 1) / kzc);
-      const double eff = (double)total / (double)(((total + sms - 1) / sms) * sms);
-      if (eff > best_eff + 1e-9) { best_eff = eff; best_kz = kzc; }
-      if (eff >= 0.95 && total >= 2LL * sms) { best_kz = kzc; break; }
-      if (kzc <= 4) break;
-    }
-    s->kz = best_kz;
-  }
+  s->kz = 0;                                        // planes per CTA of the fused stage kernels: chosen by their launcher
   if (const char* e = getenv("GX_KZ")) s->kz = std::max(1, atoi(e));
   // a user boundary functor may write ghost cells, so ghosts must be real arrays then
   for (int d = 0; d < 3; ++d) s->A.wrap[d] = (s->fused && s->periodic[d] && s->nb[d] == 1 && !c->bc_user && !getenv("GX_NO_WRAP")) ? 1 : 0;

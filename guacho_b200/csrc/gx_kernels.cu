@@ -25,17 +25,22 @@ namespace GX_NS {
 using gxp::Phys;
 
 // ---------------------------------------------------------------------------
-// block-wide min of positive doubles -> one atomicMin on the ordered bit pattern
+// block-wide min of positive doubles -> one atomicMin on the ordered bit pattern.
+// INVERSE: the threads hold 1/dt candidates (max is taken, one reciprocal per CTA).
+template <bool INVERSE = false>
 __device__ __forceinline__ void block_atomic_min(double v, unsigned long long* dst) {
-  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  auto red = [](double a, double b) { return INVERSE ? fmax(a, b) : fmin(a, b); };
+  for (int o = 16; o > 0; o >>= 1) v = red(v, __shfl_xor_sync(0xffffffffu, v, o));
   __shared__ double smin[32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int tl = (int)((threadIdx.z * blockDim.y + threadIdx.y) * blockDim.x + threadIdx.x);   // linear thread id (the flux-CD kernel uses 3-D CTAs)
+  const int lane = tl & 31, wid = tl >> 5;
   if (lane == 0) smin[wid] = v;
   __syncthreads();
   if (wid == 0) {
-    const int nw = (blockDim.x + 31) >> 5;
-    v = lane < nw ? smin[lane] : 1.e30;
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int nw = (int)((blockDim.x * blockDim.y * blockDim.z + 31) >> 5);
+    v = lane < nw ? smin[lane] : (INVERSE ? 0.0 : 1.e30);
+    for (int o = 16; o > 0; o >>= 1) v = red(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (INVERSE) v = v > 0.0 ? 1.0 / v : 1.e30;
     if (lane == 0) atomicMin(dst, (unsigned long long)__double_as_longlong(v));   // v > 0: bit order == value order
   }
 }
@@ -217,13 +222,27 @@ __global__ void __launch_bounds__(128) k_viscous(const StepArgs A, double eta, c
 // flux-CD evolution of B from the cell-centred E (flux_cd_update, src/flux_cd_module.f90:311-321),
 // the companion of the fused stage kernel; with want_cfl also the CFL candidates of the
 // finished state (get_timestep, src/hydro_core.f90:644-675).
+// A CTA is a 32 x BUY x BUZ brick of cells: the y and z neighbours of the E stencil are then read by threads of the
+// same CTA and hit L1 (read-only path) instead of being fetched again from L2 — the kernel is bound by the L2 -> SM
+// traffic of the twelve stencil reads per cell, not by DRAM (72 / 112 algorithmic bytes per cell).
+#ifndef GX_BU_Y
+#define GX_BU_Y 4
+#endif
+#ifndef GX_BU_Z
+#define GX_BU_Z 2
+#endif
 template <bool CFL>
-__global__ void __launch_bounds__(256) k_bupdate(const StepArgs A, double dt, const double* Ub, const double* __restrict__ E,
-                                                 double* dst, unsigned long long* dtmin_bits) {
+__global__ void __launch_bounds__(32 * GX_BU_Y * GX_BU_Z) k_bupdate(const StepArgs A, double dt, const double* Ub, const double* __restrict__ E,
+                                                                    double* dst, unsigned long long* dtmin_bits) {
   const Grid& g = A.g;
-  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) + 1, j = (int)blockIdx.y + 1, k = (int)blockIdx.z + A.kbeg;
+  const int i = (int)(blockIdx.x * 32 + threadIdx.x) + 1, j = (int)(blockIdx.y * GX_BU_Y + threadIdx.y) + 1;
+  const int k = (int)(blockIdx.z * GX_BU_Z + threadIdx.z) + A.kbeg;
+#if defined(GX_FLAVOUR_FAST)
+  double inv_dtp = 0.0;                           // max over cells of (|v| + c) / dx: one reciprocal per CTA instead of three divisions per cell
+#else
   double dtp = 1.e30;
-  if (i <= g.nx) {
+#endif
+  if (i <= g.nx && j <= g.ny && k <= A.klast) {
     const long long c = g.idx(i, j, k), sy = g.px, sz = (long long)g.px * g.py, vs = g.vs;
     const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
     // neighbours of the E stencil; a self-periodic direction wraps instead of reading a ghost cell
@@ -242,12 +261,24 @@ __global__ void __launch_bounds__(256) k_bupdate(const StepArgs A, double dt, co
       gxp::u2prim<true>(A.phys, u, w, 0.0, T);
       double cx, cy, cz;
       gxp::cfast3(A.phys, w[4], w[0], w[5], w[6], w[7], cx, cy, cz);
+#if defined(GX_FLAVOUR_FAST)
+      inv_dtp = gxp::gx_max(inv_dtp, (fabs(w[1]) + cx) * A.idx3[0]);
+      inv_dtp = gxp::gx_max(inv_dtp, (fabs(w[2]) + cy) * A.idx3[1]);
+      inv_dtp = gxp::gx_max(inv_dtp, (fabs(w[3]) + cz) * A.idx3[2]);
+#else
       dtp = fmin(dtp, g.dx / (fabs(w[1]) + cx));
       dtp = fmin(dtp, g.dy / (fabs(w[2]) + cy));
       dtp = fmin(dtp, g.dz / (fabs(w[3]) + cz));
+#endif
     }
   }
-  if (CFL) block_atomic_min(dtp, dtmin_bits);
+  if (CFL) {
+#if defined(GX_FLAVOUR_FAST)
+    block_atomic_min<true>(inv_dtp, dtmin_bits);
+#else
+    block_atomic_min(dtp, dtmin_bits);
+#endif
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -330,9 +361,10 @@ static int l_stage(const StepArgs& A, int order, double dt, const double* S, con
 
 static void l_bupdate(const StepArgs& A, double dt, const double* Ub, const double* E, double* dst, unsigned long long* dtmin_bits, int want_cfl, cudaStream_t s) {
   const Grid& g = A.g;
-  dim3 grid = grid_for(g.nx, g.ny, A.klast - A.kbeg + 1, 256);
-  if (want_cfl) k_bupdate<true><<<grid, 256, 0, s>>>(A, dt, Ub, E, dst, dtmin_bits);
-  else k_bupdate<false><<<grid, 256, 0, s>>>(A, dt, Ub, E, dst, dtmin_bits);
+  const dim3 block(32, GX_BU_Y, GX_BU_Z);
+  const dim3 grid((g.nx + 31) / 32, (g.ny + GX_BU_Y - 1) / GX_BU_Y, (A.klast - A.kbeg + 1 + GX_BU_Z - 1) / GX_BU_Z);
+  if (want_cfl) k_bupdate<true><<<grid, block, 0, s>>>(A, dt, Ub, E, dst, dtmin_bits);
+  else k_bupdate<false><<<grid, block, 0, s>>>(A, dt, Ub, E, dst, dtmin_bits);
 }
 
 static const KernelTable table = {l_calcprim, l_fluxes, l_efield, l_update, l_viscous, l_stage, l_bupdate};

@@ -39,6 +39,7 @@ struct StepArgs {
   int kbeg, klast;         // planes (Fortran k) the fused stage / B-update launch covers; 1..nz unless the step is split into
                            // boundary-first and interior launches to overlap the halo exchange (multi-GPU)
   gxp::Phys phys;
+  double idx3[3];          // 1/dx, 1/dy, 1/dz (production kernels: CFL candidates without divisions)
   int solver, limiter;
   int flux_cd, eight_wave, user_src;
   GravityPoints grav;
@@ -60,18 +61,12 @@ struct KernelTable {
   // fused stage (gx_stage.cu): dst = Ub - dt*div F(prim(S)) for the non-B variables (all variables
   // without flux-CD), E = cell-centred electric field of the same fluxes (flux-CD only);
   // without flux-CD and with want_cfl the CFL minimum of the new state goes to *dtmin_bits.
-  int (*stage)(const StepArgs&, int order, double dt, const double* S, const double* Ub, double* dst, double* E, int kz,
+  int (*stage)(const StepArgs&, int order, double dt, const double* S, const double* Ub, double* dst, double* E, int kz /* planes per CTA; <= 0: chosen by the launcher */,
                unsigned long long* dtmin_bits, int want_cfl, int* errflag, cudaStream_t);
   // flux-CD: dst(B) = Ub(B) - dt*curl E (central differences); want_cfl: CFL minimum of dst
   void (*bupdate)(const StepArgs&, double dt, const double* Ub, const double* E, double* dst,
                   unsigned long long* dtmin_bits, int want_cfl, cudaStream_t);
 };
-#ifndef GX_STAGE_TX
-#define GX_STAGE_TX 32
-#endif
-#ifndef GX_STAGE_TY
-#define GX_STAGE_TY 11
-#endif
 const KernelTable* kernels_strict();
 const KernelTable* kernels_fast();
 

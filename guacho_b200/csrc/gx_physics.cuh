@@ -96,13 +96,18 @@ __device__ __forceinline__ double sqrt_prod(const SqrtDen&, const SqrtDen&, doub
 // Supersonic interfaces (sl > 0 or sr < 0: the flux is the upwind physical flux) are rare.  In the production build the
 // test is made warp-uniform with one vote, which keeps the override and its reconvergence bookkeeping out of the common
 // path (measured: -6 % on the second-order stage kernel); the strict build keeps the reference's plain per-lane tests.
-#if defined(GX_FLAVOUR_FAST) && !defined(GX_NO_VOTE_SUPERSONIC)
 #ifndef GX_SOLVE_MASK            // lanes that solve together: the fused stage kernel solves with whole warps
 #define GX_SOLVE_MASK __activemask()
 #endif
+#if defined(GX_FLAVOUR_FAST) && !defined(GX_NO_VOTE_SUPERSONIC)
 #define GX_ANY_SUPERSONIC(sl, sr) __any_sync(GX_SOLVE_MASK, ((sl) > 0.0) || ((sr) < 0.0))
 #else
 #define GX_ANY_SUPERSONIC(sl, sr) true
+#endif
+#if defined(GX_FLAVOUR_FAST) && !defined(GX_NO_VOTE_DSTAR)
+#define GX_ANY_LANE(p) __any_sync(GX_SOLVE_MASK, (p))
+#else
+#define GX_ANY_LANE(p) true
 #endif
 
 // ---- u2prim: src/hydro_core.f90:46-129 (dynamic variables only; passives are copies) ----
@@ -602,19 +607,23 @@ __device__ __forceinline__ int riemann_hlld(const Phys& P, const double (&wl)[8]
   const double byL = wl[6] * nL, bzL = wl[7] * nL;
   const double byR = wr[6] * nR, bzR = wr[7] * nR;
 
-  // double-star state (hlld.f90:207-253)
-  const double idd = fast_rcp(sql + sqr), sq2 = sql * sqr;
-  const double vss = (sql * vL + sqr * vR + mul_sign(byR - byL, bx)) * idd;
-  const double wss = (sql * wLs + sqr * wRs + mul_sign(bzR - bzL, bx)) * idd;
-  const double byss = (sql * byR + sqr * byL + sq2 * mul_sign(vR - vL, bx)) * idd;
-  const double bzss = (sql * bzR + sqr * bzL + sq2 * mul_sign(wRs - wLs, bx)) * idd;
-  const double vdb_ss = sM * bx + vss * byss + wss * bzss;
-
   // region: hlld.f90 tests sstl>=0, sstr<=0, sM>=0, sM<=0 in this order
   const bool starL = sstl >= 0.0, starR = !starL && (sstr <= 0.0);
   const bool dstar = !(starL || starR);
   const bool left = starL || (dstar && sM >= 0.0);
   const int err = (dstar && !(sM >= 0.0) && !(sM <= 0.0)) ? 1 : 0;     // NaN: 'Error in HLLD routine' + stop
+
+  // double-star state (hlld.f90:207-253): formed for the whole warp when any of its interfaces lies between the
+  // two Alfven waves, skipped otherwise (faces with Bn = 0, super-Alfvenic flow)
+  double vss = 0.0, wss = 0.0, byss = 0.0, bzss = 0.0, vdb_ss = 0.0;
+  if (GX_ANY_LANE(dstar)) {
+    const double idd = fast_rcp(sql + sqr), sq2 = sql * sqr;
+    vss = (sql * vL + sqr * vR + mul_sign(byR - byL, bx)) * idd;
+    wss = (sql * wLs + sqr * wRs + mul_sign(bzR - bzL, bx)) * idd;
+    byss = (sql * byR + sqr * byL + sq2 * mul_sign(vR - vL, bx)) * idd;
+    bzss = (sql * bzR + sqr * bzL + sq2 * mul_sign(wRs - wLs, bx)) * idd;
+    vdb_ss = sM * bx + vss * byss + wss * bzss;
+  }
 
   // outer state K = L | R by select, then one energy evaluation (hlld.f90:113-114, 137-156)
   const double q0 = left ? wl[0] : wr[0], q1 = left ? wl[1] : wr[1], q2 = left ? wl[2] : wr[2], q3 = left ? wl[3] : wr[3];

@@ -47,7 +47,8 @@ def orszag_tang(p: Params, coords=(0, 0, 0), rsc: float = 1.0) -> np.ndarray:
     i, j, k = _block_index_grids(p, coords)
     x = ((i + 0.5) * p.dx * rsc)[:, None, None]
     y = ((j + 0.5) * p.dy * rsc)[None, :, None]
-    one = np.ones((i.size, j.size, k.size))
+    # the field does not depend on z: evaluate one (x, y) plane and broadcast it along z on assignment
+    one = np.ones((i.size, j.size, 1))
     vx = -np.sin(y * twopi) * one
     vy = np.sin(x * twopi) * one
     vz = 0.0 * one
