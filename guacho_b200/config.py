@@ -39,7 +39,7 @@ class GxConfig(C.Structure):
         ("enable_flux_cd", C.c_int32), ("eight_wave", C.c_int32), ("user_source_terms", C.c_int32),
         ("bc_left", C.c_int32), ("bc_right", C.c_int32), ("bc_bottom", C.c_int32),
         ("bc_top", C.c_int32), ("bc_out", C.c_int32), ("bc_in", C.c_int32),
-        ("bc_user", C.c_int32), ("strict_fp", C.c_int32), ("cooling", C.c_int32),
+        ("bc_user", C.c_int32), ("strict_fp", C.c_int32), ("cooling", C.c_int32), ("pad_", C.c_int32),
         ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double),
         ("cv", C.c_double), ("gamma", C.c_double), ("Tempsc", C.c_double),
         ("cfl", C.c_double), ("eta", C.c_double), ("tsc", C.c_double),

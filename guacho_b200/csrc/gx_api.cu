@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -12,6 +13,7 @@
 
 #include <algorithm>
 #include <string>
+#include <vector>
 #include <vector>
 
 #include "../../include/guacho_gx.h"
@@ -58,6 +60,10 @@ static int nccl_load() {
 }
 #define NCCL_TRY(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) return fail(GX_ECOMM, "%s failed: %s", #x, g_nccl.GetErrorString(r_)); } while (0)
 
+// layout of the boundary struct (include/guacho_gx.h): no implicit padding, the same image in C, ctypes and bind(C)
+static_assert(offsetof(gx_config, pad_) == 33 * 4 && offsetof(gx_config, dx) == 34 * 4 && sizeof(gx_config) == 34 * 4 + 9 * 8,
+              "gx_config layout changed: update include/guacho_gx.h, guacho_b200/config.py and guacho_b200/fortran/guacho_gpu.f90 together");
+
 // ---------------------------------------------------------------------------
 struct TimedLaunch { int cls; cudaEvent_t a, b; };
 
@@ -98,6 +104,7 @@ struct gx_solver {
   std::vector<gx_wind_sphere> spheres;                        // passed to k_wind_spheres by value (<= GX_MAX_SPHERES)
   gx_host_bc_fn host_bc = nullptr; void* host_bc_user = nullptr;
   gx_bc_hook_fn bc_hook = nullptr; void* bc_hook_user = nullptr;
+  gx_host_source_fn host_src = nullptr; void* host_src_user = nullptr;
   // diagnostics
   long long launches = 0;
   bool profiling = false;
@@ -478,13 +485,16 @@ static void launch_bc_face(gx_solver* s, double* A, int nvar, int dir, int side,
 //         flux_cd_module.f90:143-192)
 // `st`: only the overlapped step passes the halo stream, and only when every direction but z is wrapped in the loaders
 // and z goes through the peer push (no kernels of this function then run besides the physical fills at the z ends)
-static int apply_boundaries(gx_solver* s, double* A, int nvar, int nl, int kind, bool skip_wrapped = false, cudaStream_t st = nullptr) {
+// `local_only`: no exchange with other blocks (their ghost layers were filled by the last step); this is what the
+// download entry points use, so that gx_get_state / gx_get_up are NOT collective calls.
+static int apply_boundaries(gx_solver* s, double* A, int nvar, int nl, int kind, bool skip_wrapped = false, cudaStream_t st = nullptr,
+                            bool local_only = false) {
   for (int dir = 0; dir < 3; ++dir) {
     if (s->nb[dir] == 1 && s->periodic[dir]) {            // neighbour is the block itself
       if (skip_wrapped && s->A.wrap[dir]) continue;       // the fused kernels wrap their reads instead
       launch_bc_face(s, A, nvar, dir, 0, 0, nl, -1);
       launch_bc_face(s, A, nvar, dir, 1, 0, nl, -1);
-    } else {
+    } else if (!local_only) {
       int rc = exchange_dir(s, A, nvar, nl, dir, st);
       if (rc) return rc;
     }
@@ -527,10 +537,69 @@ static int apply_user_bc(gx_solver* s, double* A, int order) {
   return GX_OK;
 }
 
+// ---- slow path of get_user_source_terms for arbitrary user code (src/sources.f90:205): primitives to the host, the
+// user's callback fills s(neq, ...) in reference layout, s back to the device (into the free face-flux array), then
+// up = up + dt * s over the interior (hydro_solver.f90:115-121).  Not on any timed path.
+__global__ void k_add_source(Grid g, int nvar, double dt, const double* __restrict__ S, double* __restrict__ dst) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) + 1, j = (int)blockIdx.y + 1, k = (int)blockIdx.z + 1;
+  if (i > g.nx) return;
+  const long long c = g.idx(i, j, k);
+  for (int q = 0; q < nvar; ++q) dst[q * g.vs + c] = dst[q * g.vs + c] + dt * S[q * g.vs + c];
+}
+static int apply_host_source(gx_solver* s, double dt, double* dst) {
+  if (!s->host_src) return GX_OK;
+  const Grid& g = s->A.g;
+  const size_t n = (size_t)g.neq * (g.nx + 4) * (g.ny + 4) * (g.nz + 4);
+  std::vector<double> hw(n), hs(n, 0.0);
+  int rc = download_aos(s, s->W, hw.data(), g.neq); if (rc) return rc;
+  s->host_src(hw.data(), hs.data(), s->host_src_user);
+  rc = upload_aos(s, hs.data(), s->F, g.neq); if (rc) return rc;
+  { LaunchScope ls(s, gx::KC_UPDATE); k_add_source<<<dim3((g.nx + 127) / 128, g.ny, g.nz), 128, 0, s->stream>>>(g, g.neq, dt, s->F, dst); }
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return GX_OK;
+}
+
 // ---------------------------------------------------------------------------
 extern "C" {
 
 const char* gx_last_error(void) { return g_err.c_str(); }
+
+// prim2fhll* called directly (src/hll.f90:47, hllc.f90:44, hlle.f90:48, hlld.f90:48) for n state pairs
+int gx_riemann_flux(const gx_config* c, int32_t n, const double* wl, const double* wr, double* ff, int32_t* err) {
+  if (!c || !wl || !wr || !ff || n < 0) return fail(GX_EINVAL, "null argument");
+  if (c->struct_bytes != (int)sizeof(gx_config)) return fail(GX_EINVAL, "gx_config size mismatch");
+  if (c->neqdyn != 5 && c->neqdyn != 8) return fail(GX_EINVAL, "neqdyn must be 5 or 8");
+  const bool mhd_solver = c->riemann_solver == GX_SOLVER_HLLE || c->riemann_solver == GX_SOLVER_HLLD;
+  if (mhd_solver != (c->neqdyn == 8)) return fail(GX_EINVAL, "HLLE/HLLD need neqdyn = 8, HLL/HLLC neqdyn = 5 (SURVEY Q12)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(GX_ENODEVICE, "no CUDA device: the Riemann solvers have no CPU fallback"); }
+  if (c->device >= 0) { if (c->device >= ndev) return fail(GX_ENODEVICE, "device %d of %d", c->device, ndev); cudaSetDevice(c->device); }
+  if (n == 0) return GX_OK;
+  gxp::Phys P{};
+  P.cv = c->cv; P.gamma = c->gamma; P.Tempsc = c->Tempsc; P.inv_cv = 1.0 / c->cv; P.m4gamma = -4.0 * c->gamma;
+  P.eos = c->eq_of_state; P.neqdyn = c->neqdyn; P.npas = 0;
+  const int nq = c->neqdyn;
+  std::vector<double> hl((size_t)n * 8, 0.0), hr((size_t)n * 8, 0.0), hf((size_t)n * 8, 0.0);
+  std::vector<int> he((size_t)n, 0);
+  for (int t = 0; t < n; ++t) for (int q = 0; q < nq; ++q) { hl[(size_t)t * 8 + q] = wl[(size_t)t * nq + q]; hr[(size_t)t * 8 + q] = wr[(size_t)t * nq + q]; }
+  double *dl = nullptr, *dr = nullptr, *df = nullptr; int* de = nullptr;
+  const size_t b = (size_t)n * 8 * sizeof(double);
+  auto cleanup = [&]() { cudaFree(dl); cudaFree(dr); cudaFree(df); cudaFree(de); };
+  if (cudaMalloc((void**)&dl, b) != cudaSuccess || cudaMalloc((void**)&dr, b) != cudaSuccess || cudaMalloc((void**)&df, b) != cudaSuccess ||
+      cudaMalloc((void**)&de, (size_t)n * sizeof(int)) != cudaSuccess) { cleanup(); cudaGetLastError(); return fail(GX_ENOMEM, "cudaMalloc failed"); }
+  cudaMemcpy(dl, hl.data(), b, cudaMemcpyHostToDevice);
+  cudaMemcpy(dr, hr.data(), b, cudaMemcpyHostToDevice);
+  const gx::KernelTable* K = c->strict_fp ? gx::kernels_strict() : gx::kernels_fast();
+  int rc = K->riemann_points(P, c->riemann_solver, n, dl, dr, df, de, 0);
+  if (rc) { cleanup(); return fail(rc, "riemann solver %d not implemented", c->riemann_solver); }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { cleanup(); return fail(GX_ECUDA, "riemann kernel: %s", cudaGetErrorString(e)); }
+  cudaMemcpy(hf.data(), df, b, cudaMemcpyDeviceToHost);
+  cudaMemcpy(he.data(), de, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost);
+  cleanup();
+  for (int t = 0; t < n; ++t) { for (int q = 0; q < nq; ++q) ff[(size_t)t * nq + q] = hf[(size_t)t * 8 + q]; if (err) err[t] = he[t]; }
+  return GX_OK;
+}
 
 const char* gx_build_info(void) {
   return "libguacho_gx sm_100a; kernels: strict(-fmad=false) + fast(-fmad=true); FP64; built " __DATE__;
@@ -603,7 +672,7 @@ int gx_create(const gx_config* c, gx_solver** out) {
   s->rank = rank_of(c->cx, c->cy, c->cz);
 
 #define ALLOC(p, n) do { cudaError_t e_ = cudaMalloc((void**)&(p), (n)); if (e_ != cudaSuccess) { std::string m = cudaGetErrorString(e_); gx_destroy(s); return fail(GX_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", (size_t)(n), m.c_str()); } cudaMemsetAsync((p), 0, (n), 0); } while (0)
-  cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { s->stream = nullptr; gx_destroy(s); cudaGetLastError(); return fail(GX_ECUDA, "cudaStreamCreate failed"); }
   const size_t var_bytes = (size_t)g.vs * sizeof(double);
   // fused stage kernels cover the dynamic variables with the adiabatic equation of state; passives, the 8-wave / user sources and
   // eta != 0 (viscous_copy needs up's stale half-step ghosts) take the pass-per-routine kernels
@@ -620,7 +689,7 @@ int gx_create(const gx_config* c, gx_solver** out) {
   }
   if (c->enable_flux_cd) ALLOC(s->E, var_bytes * 3);
   ALLOC(s->dscal, sizeof(gx_solver::DevScalars));
-  cudaMallocHost((void**)&s->hscal, sizeof(gx_solver::DevScalars));
+  if (cudaMallocHost((void**)&s->hscal, sizeof(gx_solver::DevScalars)) != cudaSuccess) { s->hscal = nullptr; gx_destroy(s); cudaGetLastError(); return fail(GX_ENOMEM, "cudaMallocHost failed (pinned scalars)"); }
   // staging: up to 64 MiB or 4 planes, whichever is larger
   const size_t plane = (size_t)g.neq * (g.nx + 4) * (g.ny + 4);
   s->stage_doubles = std::max(plane * 4, std::min(plane * (size_t)(g.nz + 4), (size_t)(64u << 20) / sizeof(double)));
@@ -636,7 +705,7 @@ int gx_create(const gx_config* c, gx_solver** out) {
     for (int side = 0; side < 2; ++side) { ALLOC(s->halo_send[2 * d + side], s->halo_doubles[d] * sizeof(double)); ALLOC(s->halo_recv[2 * d + side], s->halo_doubles[d] * sizeof(double)); }
   }
 #undef ALLOC
-  cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
+  if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) { gx_destroy(s); cudaGetLastError(); return fail(GX_ECUDA, "cudaEventCreate failed"); }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { gx_destroy(s); return fail(GX_ECUDA, "device sync after allocation: %s", cudaGetErrorString(e)); }
   *out = s;
@@ -833,6 +902,7 @@ static int tstep_enqueue(gx_solver* s, double dt_cfl) {
     rc = apply_boundaries(s, s->E, 3, 1, 1); if (rc) return rc;
   }
   { LaunchScope ls(s, gx::KC_UPDATE); K->update(A, dtm, s->U, s->F, s->E, s->W, s->UP, s->stream); }      // step(dtm) :165
+  rc = apply_host_source(s, dtm, s->UP); if (rc) return rc;                // get_user_source_terms, slow path (sources.f90:205)
   rc = apply_boundaries(s, s->UP, neq, 2, 0); if (rc) return rc;          // boundaryII :169
   rc = apply_user_bc(s, s->UP, 2); if (rc) return rc;
   { LaunchScope ls(s, gx::KC_PRIM); K->calcprim(A, s->UP, s->W, nullptr, nullptr, 0, s->stream); }        // :170
@@ -844,8 +914,10 @@ static int tstep_enqueue(gx_solver* s, double dt_cfl) {
   if (s->cfg.eta == 0.0) {
     // viscous_copy with eta = 0 is u(interior) = up(interior): write the full step straight into u
     { LaunchScope ls(s, gx::KC_UPDATE); K->update(A, dt_cfl, s->U, s->F, s->E, s->W, s->U, s->stream); }
+    rc = apply_host_source(s, dt_cfl, s->U); if (rc) return rc;
   } else {
     { LaunchScope ls(s, gx::KC_UPDATE); K->update(A, dt_cfl, s->U, s->F, s->E, s->W, s->UP, s->stream); } // step(dt) :184
+    rc = apply_host_source(s, dt_cfl, s->UP); if (rc) return rc;
     { LaunchScope ls(s, gx::KC_VISC); K->viscous(A, s->cfg.eta, s->UP, s->U, s->stream); }                // :188 (stale half-step ghosts of up)
   }
   if (s->cfg.cooling == GX_COOL_H) launch_coolingh(s, dt_cfl);            // coolingh :202-204
@@ -854,9 +926,17 @@ static int tstep_enqueue(gx_solver* s, double dt_cfl) {
   return GX_OK;
 }
 
+static int check_sources(gx_solver* s) {
+  if (s->cfg.user_source_terms && s->A.grav.n == 0 && !s->host_src)
+    return fail(GX_ESTATE, "user_source_terms = 1 but no source is attached: call gx_set_gravity_points (device functor) or "
+                           "gx_register_host_source (host slow path) before stepping; the reference calls get_user_source_terms (sources.f90:205)");
+  return GX_OK;
+}
+
 int gx_tstep(gx_solver* s, double dt_cfl) {
   if (!s) return fail(GX_EINVAL, "null argument");
   if (!s->have_state) return fail(GX_ESTATE, "gx_set_state has not been called");
+  { int rcs = check_sources(s); if (rcs) return rcs; }
   cudaSetDevice(s->device);
   CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
   int rc = tstep_enqueue(s, dt_cfl); if (rc) return rc;
@@ -870,6 +950,7 @@ int gx_tstep(gx_solver* s, double dt_cfl) {
 int gx_run(gx_solver* s, int32_t n_steps, int32_t n_iter_ramp, double* time, int32_t* iter, double* last_dt) {
   if (!s || !time || !iter) return fail(GX_EINVAL, "null argument");
   if (!s->have_state) return fail(GX_ESTATE, "gx_set_state has not been called");
+  { int rcs = check_sources(s); if (rcs) return rcs; }
   cudaSetDevice(s->device);
   CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
   for (int n = 0; n < n_steps; ++n) {
@@ -893,9 +974,9 @@ int gx_get_state(gx_solver* s, double* u, double* primit, double* temp) {
   cudaSetDevice(s->device);
   const Grid& g = s->A.g;
   int rc;
-  if (s->ghosts_stale) {                              // boundaryI / boundaryII copies the fused step did not need
-    rc = apply_boundaries(s, s->U, g.neq, 1, 0); if (rc) return rc;
-    rc = apply_boundaries(s, s->UP, g.neq, 2, 0); if (rc) return rc;
+  if (s->ghosts_stale) {                              // self-periodic boundaryI / boundaryII copies the fused step did not need
+    rc = apply_boundaries(s, s->U, g.neq, 1, 0, false, nullptr, true); if (rc) return rc;      // (ghost layers owned by OTHER blocks were
+    rc = apply_boundaries(s, s->UP, g.neq, 2, 0, false, nullptr, true); if (rc) return rc;     //  exchanged by the step: no collective here)
     s->ghosts_stale = false;
   }
   if (u) { rc = download_aos(s, s->U, u, g.neq); if (rc) return rc; }
@@ -916,12 +997,19 @@ int gx_get_up(gx_solver* s, double* up) {
   cudaSetDevice(s->device);
   int rc;
   if (s->ghosts_stale) {
-    rc = apply_boundaries(s, s->U, s->A.g.neq, 1, 0); if (rc) return rc;
-    rc = apply_boundaries(s, s->UP, s->A.g.neq, 2, 0); if (rc) return rc;
+    rc = apply_boundaries(s, s->U, s->A.g.neq, 1, 0, false, nullptr, true); if (rc) return rc;
+    rc = apply_boundaries(s, s->UP, s->A.g.neq, 2, 0, false, nullptr, true); if (rc) return rc;
     s->ghosts_stale = false;
   }
   rc = download_aos(s, s->UP, up, s->A.g.neq); if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return GX_OK;
+}
+
+int gx_register_host_source(gx_solver* s, gx_host_source_fn cb, void* user) {
+  if (!s) return fail(GX_EINVAL, "null argument");
+  if (cb && !s->cfg.user_source_terms) return fail(GX_EINVAL, "gx_register_host_source needs user_source_terms = 1 (the fused kernels carry no source terms)");
+  s->host_src = cb; s->host_src_user = user;
   return GX_OK;
 }
 

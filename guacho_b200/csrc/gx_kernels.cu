@@ -282,6 +282,34 @@ __global__ void __launch_bounds__(32 * GX_BU_Y * GX_BU_Z) k_bupdate(const StepAr
 }
 
 // ---------------------------------------------------------------------------
+// Per-interface Riemann flux for n independent state pairs (prim2fhll / prim2fhllc / prim2fhlle / prim2fhlld called
+// directly: src/hll.f90:47, src/hllc.f90:44, src/hlle.f90:48, src/hlld.f90:48): the SAME device functions the sweeps use,
+// on caller-supplied (rotated) primitive states.  wl, wr, ff: [n][8] (hydro solvers use the first 5 slots).
+template <int SOLVER>
+__global__ void __launch_bounds__(128) k_riemann_points(const Phys P, int n, const double* __restrict__ wl, const double* __restrict__ wr,
+                                                        double* __restrict__ ff, int* __restrict__ err) {
+  const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (t >= n) return;
+  double l[8], r[8], f[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { l[q] = wl[8 * t + q]; r[q] = wr[8 * t + q]; f[q] = 0.0; }
+  gxp::PasInfo I;
+  err[t] = gxp::riemann<SOLVER>(P, l, r, f, I);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) ff[8 * t + q] = f[q];
+}
+static int l_riemann_points(const Phys& P, int solver, int n, const double* wl, const double* wr, double* ff, int* err, cudaStream_t s) {
+  const int nb = (n + 127) / 128;
+  switch (solver) {
+    case GX_SOLVER_HLL:  k_riemann_points<GX_SOLVER_HLL><<<nb, 128, 0, s>>>(P, n, wl, wr, ff, err); return 0;
+    case GX_SOLVER_HLLC: k_riemann_points<GX_SOLVER_HLLC><<<nb, 128, 0, s>>>(P, n, wl, wr, ff, err); return 0;
+    case GX_SOLVER_HLLE: k_riemann_points<GX_SOLVER_HLLE><<<nb, 128, 0, s>>>(P, n, wl, wr, ff, err); return 0;
+    case GX_SOLVER_HLLD: k_riemann_points<GX_SOLVER_HLLD><<<nb, 128, 0, s>>>(P, n, wl, wr, ff, err); return 0;
+  }
+  return GX_EUNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------
 // launchers
 static inline dim3 grid_for(int nxr, int nyr, int nzr, int bx) { return dim3((unsigned)((nxr + bx - 1) / bx), (unsigned)nyr, (unsigned)nzr); }
 
@@ -367,7 +395,7 @@ static void l_bupdate(const StepArgs& A, double dt, const double* Ub, const doub
   else k_bupdate<false><<<grid, block, 0, s>>>(A, dt, Ub, E, dst, dtmin_bits);
 }
 
-static const KernelTable table = {l_calcprim, l_fluxes, l_efield, l_update, l_viscous, l_stage, l_bupdate};
+static const KernelTable table = {l_calcprim, l_fluxes, l_efield, l_update, l_viscous, l_stage, l_bupdate, l_riemann_points};
 
 }  // namespace GX_NS
 

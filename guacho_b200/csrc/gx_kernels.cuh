@@ -66,6 +66,8 @@ struct KernelTable {
   // flux-CD: dst(B) = Ub(B) - dt*curl E (central differences); want_cfl: CFL minimum of dst
   void (*bupdate)(const StepArgs&, double dt, const double* Ub, const double* E, double* dst,
                   unsigned long long* dtmin_bits, int want_cfl, cudaStream_t);
+  // per-interface flux of n (rotated) primitive state pairs [n][8] (gx_riemann_flux)
+  int (*riemann_points)(const gxp::Phys&, int solver, int n, const double* wl, const double* wr, double* ff, int* err, cudaStream_t);
 };
 const KernelTable* kernels_strict();
 const KernelTable* kernels_fast();

@@ -26,9 +26,19 @@ module guacho_gpu
     integer(c_int32_t) :: riemann_solver, slope_limiter, eq_of_state
     integer(c_int32_t) :: enable_flux_cd, eight_wave, user_source_terms
     integer(c_int32_t) :: bc_left, bc_right, bc_bottom, bc_top, bc_out, bc_in
-    integer(c_int32_t) :: bc_user, strict_fp, cooling
+    integer(c_int32_t) :: bc_user, strict_fp, cooling, pad_
     real(c_double)     :: dx, dy, dz, cv, gamma, Tempsc, cfl, eta, tsc
   end type gx_config
+
+  !> image of struct gx_wind_sphere (impose_user_bc functor, EXO/exoplanet.f90:125-266)
+  type, bind(C) :: gx_wind_sphere
+    real(c_double) :: xc, yc, zc, radius
+    real(c_double) :: vwind, dens
+    real(c_double) :: tfac, temp
+    real(c_double) :: vbx, vby, vbz
+    real(c_double) :: bdip
+    real(c_double) :: pas(4)
+  end type gx_wind_sphere
 
   type(c_ptr), save :: gx_handle = c_null_ptr   !< the solver of this MPI rank
 
@@ -91,6 +101,57 @@ module guacho_gpu
       integer(c_int32_t), value :: n
       real(c_double), intent(in) :: gm(*), pos(*)
     end function
+    !> n_steps iterations of the loop body of main.f90:94-125 without output
+    integer(c_int) function gx_run(handle, n_steps, n_iter_ramp, time, iter, last_dt) bind(C, name="gx_run")
+      import :: c_int, c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: n_steps, n_iter_ramp
+      real(c_double), intent(inout) :: time
+      integer(c_int32_t), intent(inout) :: iter
+      real(c_double), intent(out) :: last_dt
+    end function
+    !> the half-step array `up` on the host (debug / parity aid)
+    integer(c_int) function gx_get_up(handle, up) bind(C, name="gx_get_up")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), intent(out) :: up(*)
+    end function
+    !> impose_user_bc as a device functor: wind spheres (EXO/exoplanet.f90:125-266)
+    integer(c_int) function gx_set_wind_spheres(handle, n, sph) bind(C, name="gx_set_wind_spheres")
+      import :: c_int, c_int32_t, c_ptr, gx_wind_sphere
+      type(c_ptr), value :: handle
+      integer(c_int32_t), value :: n
+      type(gx_wind_sphere), intent(in) :: sph(*)
+    end function
+    !> host hook at the top of every impose_user_bc application (the planet moves there, exoplanet.f90:137-144)
+    integer(c_int) function gx_register_bc_hook(handle, cb, user) bind(C, name="gx_register_bc_hook")
+      import :: c_int, c_ptr, c_funptr
+      type(c_ptr), value :: handle
+      type(c_funptr), value :: cb          !< c_funloc of a bind(C) subroutine (order, time, user)
+      type(c_ptr), value :: user
+    end function
+    !> slow paths for arbitrary user code: impose_user_bc(u, order) / get_user_source_terms on host arrays
+    integer(c_int) function gx_register_host_bc(handle, cb, user) bind(C, name="gx_register_host_bc")
+      import :: c_int, c_ptr, c_funptr
+      type(c_ptr), value :: handle
+      type(c_funptr), value :: cb          !< bind(C) subroutine (u, order, user)
+      type(c_ptr), value :: user
+    end function
+    integer(c_int) function gx_register_host_source(handle, cb, user) bind(C, name="gx_register_host_source")
+      import :: c_int, c_ptr, c_funptr
+      type(c_ptr), value :: handle
+      type(c_funptr), value :: cb          !< bind(C) subroutine (primit, s, user)
+      type(c_ptr), value :: user
+    end function
+    !> prim2fhll / prim2fhllc / prim2fhlle / prim2fhlld for n interfaces on the device
+    integer(c_int) function gx_riemann_flux(cfg, n, wl, wr, ff, err) bind(C, name="gx_riemann_flux")
+      import :: c_int, c_int32_t, c_double, c_ptr, gx_config
+      type(gx_config), intent(in) :: cfg
+      integer(c_int32_t), value :: n
+      real(c_double), intent(in) :: wl(*), wr(*)
+      real(c_double), intent(out) :: ff(*)
+      type(c_ptr), value :: err            !< c_loc of an integer(c_int32_t) array, or c_null_ptr
+    end function
     type(c_ptr) function gx_last_error() bind(C, name="gx_last_error")
       import :: c_ptr
     end function
@@ -136,10 +197,32 @@ contains
     c%bc_user = merge(1, 0, bc_user)
     c%strict_fp = 0
     c%cooling = merge(cooling, 0, cooling == COOL_H)   ! the other cooling modules stay in the host
+    c%pad_ = 0
     c%dx = dx; c%dy = dy; c%dz = dz
     c%cv = cv; c%gamma = gamma; c%Tempsc = Tempsc; c%cfl = cfl; c%eta = eta; c%tsc = tsc
     call gx_check(gx_create(c, gx_handle), 'gx_create')
   end subroutine gx_initmain
+
+  !> slow path of get_user_source_terms for arbitrary user code: register with
+  !>   call gx_check(gx_register_host_source(gx_handle, c_funloc(gx_host_source_tramp), c_null_ptr), 'host source')
+  !> The library calls it once per stage with the block's primitives; the loop below is the one of
+  !> step() (hydro_solver.f90:99-121) around the user's own get_user_source_terms (user_mod.f90).
+  subroutine gx_host_source_tramp(primit_c, s_c, user) bind(C)
+    use parameters, only : neq, nx, ny, nz, nxmin, nxmax, nymin, nymax, nzmin, nzmax
+    use user_mod, only : get_user_source_terms
+    type(c_ptr), value :: primit_c, s_c, user
+    real(c_double), pointer :: pp(:,:,:,:), ss(:,:,:,:)
+    integer :: i, j, k
+    call c_f_pointer(primit_c, pp, [neq, nxmax-nxmin+1, nymax-nymin+1, nzmax-nzmin+1])
+    call c_f_pointer(s_c, ss, [neq, nxmax-nxmin+1, nymax-nymin+1, nzmax-nzmin+1])
+    do k = 1, nz
+      do j = 1, ny
+        do i = 1, nx          ! array index = Fortran index - nxmin + 1
+          call get_user_source_terms(pp(:, i-nxmin+1, j-nymin+1, k-nzmin+1), ss(:, i-nxmin+1, j-nymin+1, k-nzmin+1), i, j, k)
+        end do
+      end do
+    end do
+  end subroutine gx_host_source_tramp
 
 #ifdef MPIP
   !> replaces mpi_cart_create's role for the halo exchange: NCCL communicator over the same ranks

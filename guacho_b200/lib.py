@@ -22,8 +22,9 @@ ERRORS = {-1: "GX_EINVAL", -2: "GX_ENODEVICE", -3: "GX_ECUDA", -4: "GX_ENOMEM",
 EXPORTS = (
     "gx_create", "gx_destroy", "gx_set_state", "gx_set_time", "gx_get_timestep", "gx_tstep", "gx_run",
     "gx_get_state", "gx_get_up", "gx_set_gravity_points", "gx_set_wind_spheres", "gx_register_host_bc", "gx_register_bc_hook",
+    "gx_register_host_source",
     "gx_comm_unique_id", "gx_comm_attach", "gx_last_error", "gx_launch_count", "gx_last_elapsed_ms",
-    "gx_kernel_time_ms", "gx_set_profiling", "gx_build_info",
+    "gx_kernel_time_ms", "gx_set_profiling", "gx_build_info", "gx_riemann_flux",
 )
 
 KERNEL_CLASSES = ("flux", "update", "efield", "prim", "bc", "xpose", "visc", "stage1", "stage2", "bupdate")
@@ -44,6 +45,7 @@ class WindSphere(C.Structure):
 
 HOST_BC_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int32, C.c_void_p)
 BC_HOOK_FN = C.CFUNCTYPE(None, C.c_int32, C.c_double, C.c_void_p)
+HOST_SOURCE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p)
 
 _lib = None
 
@@ -73,6 +75,7 @@ def load() -> C.CDLL:
     L.gx_set_wind_spheres.argtypes = [vp, C.c_int32, C.POINTER(WindSphere)]
     L.gx_register_host_bc.argtypes = [vp, HOST_BC_FN, vp]
     L.gx_register_bc_hook.argtypes = [vp, BC_HOOK_FN, vp]
+    L.gx_register_host_source.argtypes = [vp, HOST_SOURCE_FN, vp]
     L.gx_comm_unique_id.argtypes = [vp, C.c_int32]
     L.gx_comm_attach.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32]
     L.gx_last_error.restype = C.c_char_p
@@ -83,6 +86,7 @@ def load() -> C.CDLL:
     L.gx_kernel_time_ms.argtypes = [vp, C.c_int32, dp, C.POINTER(C.c_int64)]
     L.gx_set_profiling.argtypes = [vp, C.c_int32]
     L.gx_build_info.restype = C.c_char_p
+    L.gx_riemann_flux.argtypes = [C.POINTER(GxConfig), C.c_int32, dp, dp, dp, C.POINTER(C.c_int32)]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int:   # default: int status

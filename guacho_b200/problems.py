@@ -85,7 +85,7 @@ def mhd_blast(p: Params, coords=(0, 0, 0), r0: float = 0.1, p_in: float = 10.0, 
                         passives=[one * (0.1 + 0.2 * q) for q in range(p.npas)])
 
 
-def smooth_random(p: Params, coords=(0, 0, 0), seed: int = 12345, kmax: int = 8, amp: float = 0.2) -> np.ndarray:
+def smooth_random(p: Params, coords=(0, 0, 0), seed: int = 12345, kmax: int = 8, amp: float = 0.2, vamp: float = 0.5) -> np.ndarray:
     """Branch-coverage field (builder-defined): periodic low-pass
     (|k|<=kmax) random perturbations, rho=1+amp*xi1, p=1+amp*xi2, v=0.5*xi3..5,
     B=0.5*xi6..8.  Built from a fixed set of Fourier modes so that any block of any
@@ -110,7 +110,7 @@ def smooth_random(p: Params, coords=(0, 0, 0), seed: int = 12345, kmax: int = 8,
 
     rho = 1.0 + amp * xi(0)
     pres = 1.0 + amp * xi(1)
-    vx, vy, vz = 0.5 * xi(2), 0.5 * xi(3), 0.5 * xi(4)
+    vx, vy, vz = vamp * xi(2), vamp * xi(3), vamp * xi(4)      # vamp >~ 3: supersonic interfaces (sl > 0 / sr < 0 branches of the solvers)
     bx, by, bz = 0.5 * xi(5), 0.5 * xi(6), 0.5 * xi(7)
     pas = [rho * (0.5 + 0.2 * xi(8 + q)) for q in range(p.npas)]
     return prim_to_cons(p, rho, vx, vy, vz, pres, bx, by, bz, passives=pas)

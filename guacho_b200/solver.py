@@ -27,6 +27,22 @@ def _dp(a: Optional[np.ndarray]):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+def riemann_flux(params: Params, wl: np.ndarray, wr: np.ndarray):
+    """prim2fhll / prim2fhllc / prim2fhlle / prim2fhlld (src/hll.f90:47, hllc.f90:44, hlle.f90:48, hlld.f90:48) for n interfaces
+    on the device: wl, wr of shape (n, neqdyn), rotated primitive states -> (flux (n, neqdyn), err (n,))."""
+    L = _lib.load()
+    wl = np.ascontiguousarray(wl, dtype=np.float64)
+    wr = np.ascontiguousarray(wr, dtype=np.float64)
+    if wl.shape != wr.shape or wl.ndim != 2 or wl.shape[1] != params.neqdyn:
+        raise ValueError(f"wl, wr must both have shape (n, {params.neqdyn})")
+    n = wl.shape[0]
+    ff = np.zeros_like(wl)
+    err = np.zeros(n, dtype=np.int32)
+    cfg = params.to_c((0, 0, 0))
+    check(L.gx_riemann_flux(C.byref(cfg), n, _dp(wl), _dp(wr), _dp(ff), err.ctypes.data_as(C.POINTER(C.c_int32))))
+    return ff, err
+
+
 class Block:
     """One block of the domain on one GPU (reference: one MPI rank)."""
 
@@ -40,6 +56,9 @@ class Block:
         check(self.L.gx_create(C.byref(self._cfg), C.byref(h)))
         self.h = h
         self._host_bc_ref = None
+        self._bc_hook_ref = None
+        self._host_src_ref = None
+        self._cb_error = None        # exception raised inside a user callback (ctypes would print and swallow it)
 
     # -- lifetime --
     def close(self) -> None:
@@ -79,7 +98,7 @@ class Block:
         if u.shape != self.shape:
             raise ValueError(f"u has shape {u.shape}, expected {self.shape}")
         a = np.asfortranarray(u, dtype=np.float64)
-        check(self.L.gx_set_state(self.h, _dp(a)))
+        self._check(self.L.gx_set_state(self.h, _dp(a)))
 
     def set_time(self, time: float) -> None:
         check(self.L.gx_set_time(self.h, float(time)))
@@ -93,14 +112,14 @@ class Block:
 
     def tstep(self, dt_cfl: float) -> None:
         """tstep (hydro_solver.f90:134-229)."""
-        check(self.L.gx_tstep(self.h, float(dt_cfl)))
+        self._check(self.L.gx_tstep(self.h, float(dt_cfl)))
 
     def run(self, n_steps: int, time: float, it: int, n_iter_ramp: int = 10):
         """n_steps iterations of main.f90's loop body, without output -> (time, iter, last_dt)."""
         t = C.c_double(time)
         i = C.c_int32(it)
         last = C.c_double(0.0)
-        check(self.L.gx_run(self.h, n_steps, n_iter_ramp, C.byref(t), C.byref(i), C.byref(last)))
+        self._check(self.L.gx_run(self.h, n_steps, n_iter_ramp, C.byref(t), C.byref(i), C.byref(last)))
         return t.value, i.value, last.value
 
     def get_state(self, u: bool = True, primit: bool = False, temp: bool = False):
@@ -140,9 +159,12 @@ class Block:
         shape = self.shape
 
         def tramp(ptr, order, _user):
-            n = int(np.prod(shape))
-            arr = np.ctypeslib.as_array(ptr, shape=(n,)).reshape(shape, order="F")
-            fn(arr, int(order))
+            try:
+                n = int(np.prod(shape))
+                arr = np.ctypeslib.as_array(ptr, shape=(n,)).reshape(shape, order="F")
+                fn(arr, int(order))
+            except BaseException as e:       # re-raised by _check after the C call returns
+                self._cb_error = self._cb_error or e
 
         self._host_bc_ref = _lib.HOST_BC_FN(tramp)
         check(self.L.gx_register_host_bc(self.h, self._host_bc_ref, None))
@@ -154,8 +176,42 @@ class Block:
             self._bc_hook_ref = None
             check(self.L.gx_register_bc_hook(self.h, _lib.BC_HOOK_FN(0), None))
             return
-        self._bc_hook_ref = _lib.BC_HOOK_FN(lambda order, time, _user: fn(int(order), float(time)))
+        def tramp(order, time, _user):
+            try:
+                fn(int(order), float(time))
+            except BaseException as e:
+                self._cb_error = self._cb_error or e
+
+        self._bc_hook_ref = _lib.BC_HOOK_FN(tramp)
         check(self.L.gx_register_bc_hook(self.h, self._bc_hook_ref, None))
+
+    def register_host_source(self, fn: Optional[Callable[[np.ndarray, np.ndarray], None]]) -> None:
+        """Slow path mirroring get_user_source_terms (src/sources.f90:205): once per stage `fn(primit, s)` gets the block's
+        primitives and a zero-filled source array, both (neq, nx+4, ny+4, nz+4) in reference layout, and adds to `s`."""
+        if fn is None:
+            self._host_src_ref = None
+            check(self.L.gx_register_host_source(self.h, _lib.HOST_SOURCE_FN(0), None))
+            return
+        shape = self.shape
+
+        def tramp(pw, ps, _user):
+            try:
+                n = int(np.prod(shape))
+                w = np.ctypeslib.as_array(pw, shape=(n,)).reshape(shape, order="F")
+                sarr = np.ctypeslib.as_array(ps, shape=(n,)).reshape(shape, order="F")
+                fn(w, sarr)
+            except BaseException as e:
+                self._cb_error = self._cb_error or e
+
+        self._host_src_ref = _lib.HOST_SOURCE_FN(tramp)
+        check(self.L.gx_register_host_source(self.h, self._host_src_ref, None))
+
+    def _check(self, rc: int) -> None:
+        """check() for the calls that may run user callbacks: an exception raised inside one is re-raised here."""
+        err, self._cb_error = self._cb_error, None
+        if err is not None:
+            raise err
+        check(rc)
 
     # -- multi-GPU --
     @staticmethod

@@ -51,8 +51,9 @@ enum { GX_OK = 0, GX_EINVAL = -1, GX_ENODEVICE = -2, GX_ECUDA = -3, GX_ENOMEM = 
 
 /* Every Fortran `parameter` the step reads (OT/parameters.f90:48-227) plus the
  * block decomposition that replaces MPI_NBX/NBY/NBZ and mpi_cart_coords
- * (src/init.f90:103-110).  Plain int32/double, no padding surprises: all
- * int32 first (even count), then doubles. */
+ * (src/init.f90:103-110).  Plain int32/double, no implicit padding: 34 int32 first
+ * (33 parameters + one explicit pad word, so the doubles start on an 8-byte offset in
+ * every binding, packed or not), then 9 doubles; gx_api.cu static_asserts the offsets. */
 typedef struct gx_config {
   int32_t struct_bytes;      /* = sizeof(gx_config); ABI check                         */
   int32_t device;            /* CUDA device ordinal; -1 = keep the current device     */
@@ -73,6 +74,7 @@ typedef struct gx_config {
   int32_t cooling;           /* GX_COOL_*: NONE, or H = the parametrised hydrogen cooling operator
                                 (src/cooling_h.f90:41-67, applied after viscous_copy, hydro_solver.f90:202-204);
                                 it needs EOS_H_RATE-style passives (npas >= 1: neutral H density)   */
+  int32_t pad_;              /* explicit padding word (keeps the int32 count even); set to 0                  */
   double dx, dy, dz;         /* globals dx dy dz (src/init.f90:120-122)               */
   double cv, gamma;          /* parameters.f90: cv, gamma=(cv+1)/cv                   */
   double Tempsc;             /* temperature scaling used by u2prim                    */
@@ -118,7 +120,8 @@ GX_API int gx_run(gx_solver* s, int32_t n_steps, int32_t n_iter_ramp, double* ti
            double* last_dt);
 
 /* Implicit "state is on the host" before write_output (src/main.f90:85,112):
- * fills caller arrays in reference layout.  Any pointer may be NULL.
+ * fills caller arrays in reference layout.  Any pointer may be NULL.  NOT collective: a rank may call it on its own
+ * (ghost layers owned by other blocks hold what the last step exchanged; only self-periodic copies are refreshed).
  *   u      : (neq, nx+4, ny+4, nz+4)   conserved, as after boundaryI
  *   primit : (neq, nx+4, ny+4, nz+4)   calcprim(u, primit) over the whole array
  *   temp   : (nx+4, ny+4, nz+4)        Temp from u2prim                         */
@@ -165,6 +168,16 @@ GX_API int gx_register_bc_hook(gx_solver* s, gx_bc_hook_fn cb, void* user);
 typedef void (*gx_host_bc_fn)(double* u, int32_t order, void* user);
 GX_API int gx_register_host_bc(gx_solver* s, gx_host_bc_fn cb, void* user);
 
+/* Slow path of get_user_source_terms(pp, s, i, j, k) (src/sources.f90:205, OT/user_mod.f90:111) for arbitrary user code:
+ * once per stage the library hands the callback the primitives of the block in reference layout,
+ * primit(neq, nx+4, ny+4, nz+4), and a zero-filled s of the same shape; the callback adds its source terms for the
+ * physical cells (a Fortran host loops i, j, k over 1..n and calls its own get_user_source_terms(primit(:,i,j,k),
+ * s(:,i,j,k), i, j, k)); the library then applies up = up + dt * s (src/hydro_solver.f90:115-121).  Device -> host ->
+ * callback -> device on every stage: excluded from any timed path.  With user_source_terms = 1 and neither this callback
+ * nor gx_set_gravity_points, gx_tstep / gx_run fail with GX_ESTATE (never a silent no-op). */
+typedef void (*gx_host_source_fn)(const double* primit, double* s, void* user);
+GX_API int gx_register_host_source(gx_solver* s, gx_host_source_fn cb, void* user);
+
 /* ---- multi-GPU: replaces mpi_cart_create / mpi_sendrecv / mpi_allreduce
  * (src/init.f90:103-110, src/boundaries.f90:77-99,292-314,
  *  src/flux_cd_module.f90:75-97, src/hydro_core.f90:685) with NCCL over NVLink.
@@ -174,6 +187,15 @@ GX_API int gx_register_host_bc(gx_solver* s, gx_host_bc_fn cb, void* user);
  * the Python host). */
 GX_API int gx_comm_unique_id(void* id_out, int32_t nbytes);
 GX_API int gx_comm_attach(gx_solver* s, const void* id, int32_t nbytes, int32_t rank, int32_t nranks);
+
+/* ---- per-interface entry point ----
+ * Replaces a direct call of prim2fhll / prim2fhllc / prim2fhlle / prim2fhlld (src/hll.f90:47-82, src/hllc.f90:44-140,
+ * src/hlle.f90:48-83, src/hlld.f90:48-319) for n independent interfaces: wl, wr = primitive states either side,
+ * already rotated into the sweep direction (swapy/swapz, src/hydro_core.f90:485-534), [n][neqdyn] with neqdyn fastest
+ * (HOST memory); ff = the flux, same shape; err[t] = 1 where the reference would print 'Error in HLLD/hllc routine' and
+ * stop (NULL: not wanted).  Uses cfg->riemann_solver, neqdyn, cv, gamma, strict_fp and device; runs the same device
+ * functions as the sweeps of gx_tstep (no CPU fallback). */
+GX_API int gx_riemann_flux(const gx_config* cfg, int32_t n, const double* wl, const double* wr, double* ff, int32_t* err);
 
 /* ---- diagnostics ---- */
 GX_API const char* gx_last_error(void);

@@ -25,6 +25,9 @@ def _run(nb, grid, nsteps, problem, strict=False, port=29541, extra=()):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "OK" in r.stdout
+    for ln in r.stdout.splitlines():
+        if ln.startswith("MGPU"):
+            print(ln)                    # kept in the log of `pytest -s` (profiles/r2_multigpu_tests_8gpu.log)
 
 
 @pytest.mark.parametrize("nb", [(1, 1, 2), (2, 1, 1), (1, 2, 1)])
@@ -54,3 +57,28 @@ def test_four_gpu_z_slabs_bitwise():
     if _ngpu() < 4:
         pytest.skip("needs 4 GPUs")
     _run((1, 1, 4), (64, 48, 80), 3, "random", port=29546)
+
+
+def test_eight_gpu_z_slabs_bitwise():
+    """Eight z slabs, periodic — the decomposition of the driver's 1 -> 8 GPU scaling run (bench.py --gpus 8): peer-memory
+    push over NVLink overlapped with the interior launches; the gathered state equals the single-block run bitwise."""
+    if _ngpu() < 8:
+        pytest.skip("needs 8 GPUs")
+    _run((1, 1, 8), (64, 48, 192), 3, "random", port=29547)
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_two_gpu_viscosity_matches_the_oracle_on_the_same_blocks(strict):
+    """eta != 0 on two GPUs.  viscous_copy (src/hydro_solver.f90:54-63) reads up's ghost cells, which still hold the
+    HALF-step halo exchanged by boundaryII (:169) while the interior holds full-step values (:188), so the
+    reference's result depends on the block decomposition next to every internal face.  The contract is therefore
+    equality with the reference run on the SAME block grid: the oracle with MPI_NBZ = 2."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run((1, 1, 2), (48, 40, 32), 3, "random", strict=strict, port=29548, extra=("eta", "oracle"))
+
+
+def test_two_gpu_y_blocks_viscosity_matches_the_oracle_on_the_same_blocks():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run((1, 2, 1), (48, 40, 32), 3, "random", strict=True, port=29549, extra=("eta", "oracle"))

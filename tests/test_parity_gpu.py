@@ -58,10 +58,93 @@ def test_solvers_random_field_3d(solver, mhd, cd, strict):
     assert err.max() <= TOL, err
 
 
+@pytest.mark.parametrize("strict", [True, False])
 @pytest.mark.parametrize("lim", ALL_LIMITERS)
-def test_limiters(lim):
-    p = Params(nxtot=24, nytot=20, nztot=16, zmax=1.0, slope_limiter=lim, strict_fp=True)
+def test_limiters(lim, strict):
+    """All eight slope limiters (src/hydro_core.f90:735-796), bit-comparison and production flavours (the production
+    build has its own select-based minmod)."""
+    p = Params(nxtot=24, nytot=20, nztot=16, zmax=1.0, slope_limiter=lim, strict_fp=strict)
     ug, uo, _, _ = run_pair(p, "random", nsteps=2)
+    assert rel_err_per_var(ug, uo).max() <= TOL
+
+
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("mhd", [True, False])
+def test_eos_single_specie(mhd, strict):
+    """EOS_SINGLE_SPECIE branch of u2prim (src/hydro_core.f90:92-100: T floored at 1 K and the pressure re-set from it).
+    Tempsc is chosen so that the floor is active in part of the field (T = p/rho*Tempsc crosses 1)."""
+    from guacho_b200.config import EOS_SINGLE_SPECIE
+    p = Params(nxtot=24, nytot=20, nztot=16, zmax=1.0, mhd=mhd, riemann_solver=SOLVER_HLLD if mhd else SOLVER_HLLC,
+               enable_flux_cd=mhd, eq_of_state=EOS_SINGLE_SPECIE, Tempsc=1.0, strict_fp=strict)
+    from guacho_b200.solver import Block
+    g = global_ic(p, "random", amp=0.45)
+    o = oracle_from_ic(p, g)
+    wo0 = interior(o.get_block(0, PRIMIT))
+    t0 = wo0[4] / wo0[0] * p.Tempsc
+    ug, uo, wg, wo = run_pair(p, "random", nsteps=2, amp=0.45)
+    assert (np.abs(wo0[4] - 1.0 * wo0[0] / p.Tempsc) < 1e-14).any() or (t0 < 1.0001).any(), "temperature floor never active: the branch is not exercised"
+    assert rel_err_per_var(ug, uo).max() <= TOL
+    assert rel_err_per_var(wg, wo).max() <= TOL
+
+
+# ---- per-interface: the device Riemann solvers on the published fixture (all six HLLD regions, both supersonic ones) ----
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("key,solver,mhd", [("hlld", SOLVER_HLLD, True), ("hlle", SOLVER_HLLE, True),
+                                            ("hll", SOLVER_HLL, False), ("hllc", SOLVER_HLLC, False)])
+def test_device_riemann_matches_published_flux_and_oracle(key, solver, mhd, strict):
+    """gx_riemann_flux (the device functions the sweeps call) on tests/golden/published_riemann.npz: 1024 interfaces covering
+    every wave region (>= 30 per HLLD region, Mach up to 2.5) against the published flux formulae (1e-11 of the flux scale)
+    and against the oracle's prim2fhll* (1e-12; the strict flavour bitwise)."""
+    import os
+    from guacho_b200.solver import riemann_flux
+    from tests.oracle_lib import Oracle
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "published_riemann.npz"))
+    p = Params(nxtot=8, nytot=8, nztot=8, mhd=mhd, riemann_solver=solver, enable_flux_cd=False, strict_fp=strict)
+    nq = p.neqdyn
+    WL, WR = np.ascontiguousarray(g["WL"][:nq].T), np.ascontiguousarray(g["WR"][:nq].T)
+    ff, err = riemann_flux(p, WL, WR)
+    assert not err.any()
+    ref = g[key].T
+    scale = np.abs(ref).max(axis=1, keepdims=True) + 1.0
+    assert (np.abs(ff - ref) / scale).max() <= 1e-11
+    o = Oracle(p)
+    fo = np.array([o.riemann(WL[m], WR[m])[0] for m in range(WL.shape[0])])
+    d = (np.abs(ff - fo) / scale).max()
+    assert d <= (0.0 if strict else 1e-12), d
+    if key == "hlld":
+        reg = g["hlld_region"]
+        assert (np.bincount(reg, minlength=6) >= 30).all()
+        for r in range(6):          # every region on its own, so that a wrong branch cannot hide behind the others
+            m = reg == r
+            assert (np.abs(ff[m] - ref[m]) / scale[m]).max() <= 1e-11, r
+
+
+def _supersonic_x_faces(w, gamma):
+    """number of x interfaces whose Davis speeds put the whole fan on one side (sl > 0 or sr < 0), first-order states"""
+    rho, vx, pr = w[0], w[1], w[4]
+    if w.shape[0] >= 8:
+        b2 = w[5] ** 2 + w[6] ** 2 + w[7] ** 2
+        a = (gamma * pr + b2) / rho
+        cf = np.sqrt(0.5 * (a + np.sqrt(np.maximum(a * a - 4 * gamma * pr * w[5] ** 2 / rho ** 2, 0.0))))
+    else:
+        cf = np.sqrt(gamma * pr / rho)
+    sl = np.minimum(vx[:-1] - cf[:-1], vx[1:] - cf[1:])
+    sr = np.maximum(vx[:-1] + cf[:-1], vx[1:] + cf[1:])
+    return int(((sl > 0) | (sr < 0)).sum())
+
+
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("solver,mhd,cd", [(SOLVER_HLLD, True, True), (SOLVER_HLLE, True, True), (SOLVER_HLLC, False, False), (SOLVER_HLL, False, False)])
+def test_supersonic_field_fires_the_upwind_branches(solver, mhd, cd, strict):
+    """A smooth random field with |v| up to ~8 sound speeds: thousands of interfaces take the sl > 0 / sr < 0 branches
+    (src/hlld.f90:70-80 and twins), i.e. the warp-vote override of the production solvers fires inside the fused stage
+    kernel — asserted by counting such faces in the oracle's primitives."""
+    p = Params(nxtot=32, nytot=24, nztot=20, zmax=1.0, mhd=mhd, riemann_solver=solver, enable_flux_cd=cd, strict_fp=strict, cfl=0.2)
+    g = global_ic(p, "random", vamp=4.0)
+    o = oracle_from_ic(p, g)
+    nsup = _supersonic_x_faces(interior(o.get_block(0, PRIMIT)), p.gamma)
+    assert nsup >= 1000, nsup
+    ug, uo, _, _ = run_pair(p, "random", nsteps=3, vamp=4.0)
     assert rel_err_per_var(ug, uo).max() <= TOL
 
 
@@ -135,6 +218,31 @@ def test_full_size_256_cubed_properties():
     assert rel_err_per_var(out[False], out[True]).max() <= TOL
 
 
+def test_bench_workload_256_cubed_against_the_oracle():
+    """BASELINE.json configs[1] at its full size, directly against the oracle: 3-D Orszag-Tang 256^3, HLLD + flux-CD, two steps
+    of the production kernels vs 16 oracle blocks (one per host thread, like the reference's MPI ranks)."""
+    from guacho_b200.solver import Block
+    from guacho_b200.config import ot_3d
+    n = 256
+    p = ot_3d(n)
+    g = global_ic(p, "ot")
+    o = oracle_from_ic(p.replace(MPI_NBX=16), g, threads=16)
+    with Block(p) as b:
+        b.set_state(g)
+        t, it = 0.0, 1
+        for _ in range(2):
+            dt_o, _ = o.get_timestep(it, 10, t, 1e300)
+            dt_g, _ = b.get_timestep(it, 10, t, 1e300)
+            assert abs(dt_g - dt_o) <= 1e-13 * dt_o
+            assert o.tstep(dt_o) == 0
+            b.tstep(dt_o)
+            t += dt_o; it += 1
+        ug = interior(b.get_state())
+    uo = o.gather(U)
+    err = rel_err_per_var(ug, uo)
+    assert err.max() <= TOL, err
+
+
 # ---- full Orszag-Tang run (north_star: "within a stated L1 tolerance over a full Orszag-Tang run") ----
 OT_FULL_L1_TOL = 1e-11     # stated tolerance, relative L1 per conserved variable at t = 0.5; measured on B200: <= 9.2e-13
                            # over 1635 steps (production FMA/shared-reciprocal kernels vs the no-FMA oracle), DESIGN.md §4
@@ -174,3 +282,87 @@ def test_full_orszag_tang_run_L1():
     assert np.abs(ug[3]).max() <= 1e-9 and np.abs(ug[7]).max() <= 1e-9      # vz = Bz = 0 stays 0 (2.5-D problem)
     rho = ug[0]
     assert 0.05 < rho.min() and rho.max() < 0.55                             # OT/plots.py:27 colour range for rho at t = 0.5
+
+
+# ---- get_user_source_terms: device functor, host slow path, and the error when neither is attached ----
+def test_user_source_without_a_functor_is_an_error_not_a_no_op():
+    """user_source_terms = 1 makes the reference call get_user_source_terms for every cell (src/sources.f90:205); the
+    library refuses to step until a source is attached instead of silently dropping it."""
+    from guacho_b200.solver import Block
+    from guacho_b200.lib import GxError
+    p = Params(nxtot=16, nytot=12, nztot=8, zmax=0.5, user_source_terms=True, strict_fp=True)
+    g = global_ic(p, "random")
+    with Block(p) as b:
+        b.set_state(g)
+        dt, _ = b.get_timestep(1, 10, 0.0, 1e300)
+        with pytest.raises(GxError, match="GX_ESTATE"):
+            b.tstep(dt)
+        with pytest.raises(GxError, match="GX_ESTATE"):
+            b.run(1, 0.0, 1)
+
+
+@pytest.mark.parametrize("mhd", [True, False])
+def test_host_source_slow_path_matches_the_device_gravity_functor(mhd):
+    """gx_register_host_source (arbitrary user code on host arrays, once per stage) against the device functor
+    gx_set_gravity_points on the same point mass: s(2:4) -= rho GM r/|r|^3, s(5) -= rho GM (v.r)/|r|^3 with the cell-centre
+    convention of EXO/user_mod.f90:174-204."""
+    from guacho_b200.solver import Block
+    p = Params(nxtot=24, nytot=20, nztot=16, zmax=1.0, mhd=mhd, riemann_solver=SOLVER_HLLD if mhd else SOLVER_HLLC,
+               enable_flux_cd=mhd, user_source_terms=True, strict_fp=True)
+    g = global_ic(p, "random")
+    gm, pos = 0.05, (0.013, -0.021, 0.017)
+
+    def gravity(w, s):          # what a user's get_user_source_terms does, vectorised over the block
+        i = (np.arange(-1, p.nx + 3) - p.nxtot / 2 - 0.5) * p.dx - pos[0]
+        j = (np.arange(-1, p.ny + 3) - p.nytot / 2 - 0.5) * p.dy - pos[1]
+        k = (np.arange(-1, p.nz + 3) - p.nztot / 2 - 0.5) * p.dz - pos[2]
+        x, y, z = i[:, None, None], j[None, :, None], k[None, None, :]
+        r15 = (x * x + y * y + z * z) ** 1.5
+        s[1] -= w[0] * gm * x / r15
+        s[2] -= w[0] * gm * y / r15
+        s[3] -= w[0] * gm * z / r15
+        s[4] -= w[0] * gm * (w[1] * x + w[2] * y + w[3] * z) / r15
+
+    out = []
+    for use_host in (False, True):
+        with Block(p) as b:
+            if use_host:
+                b.register_host_source(gravity)
+            else:
+                b.set_gravity_points([gm], [pos])
+            b.set_state(g)
+            t, it = 0.0, 1
+            for _ in range(2):
+                dt, _d = b.get_timestep(it, 10, t, 1e300)
+                b.tstep(dt)
+                t += dt; it += 1
+            out.append(interior(b.get_state()))
+    assert np.abs(out[0] - interior(g)).max() > 1e-6                      # the step did something
+    assert rel_err_per_var(out[1], out[0]).max() <= TOL
+    p0 = p.replace(user_source_terms=False)
+    with Block(p0) as b:                                                   # and the source is not a no-op
+        b.set_state(g)
+        dt, _d = b.get_timestep(1, 10, 0.0, 1e300)
+        b.tstep(dt)
+        nosrc = interior(b.get_state())
+    with Block(p) as b:
+        b.set_gravity_points([gm], [pos])
+        b.set_state(g)
+        b.tstep(dt)
+        assert np.abs(interior(b.get_state())[1:5] - nosrc[1:5]).max() > 1e-9
+
+
+def test_exception_in_a_user_callback_is_raised_not_swallowed():
+    from guacho_b200.solver import Block
+    p = Params(nxtot=16, nytot=12, nztot=8, zmax=0.5, user_source_terms=True, strict_fp=True)
+    g = global_ic(p, "random")
+
+    def bad(w, s):
+        raise ValueError("user code failed")
+
+    with Block(p) as b:
+        b.register_host_source(bad)
+        b.set_state(g)
+        dt, _ = b.get_timestep(1, 10, 0.0, 1e300)
+        with pytest.raises(ValueError, match="user code failed"):
+            b.tstep(dt)
