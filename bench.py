@@ -157,6 +157,33 @@ def workload_name(n: int, strong: bool, solver: str, flux_cd: bool) -> str:
             + ", " + solver.upper() + (" + flux-CD" if flux_cd else "") + ", minmod, periodic, cfl 0.2")
 
 
+def exo_cpu_reference(steps: int, warmup: int, threads: int, scale: float = 1.0):
+    """EXO as shipped on the oracle (its restatement of EXO/user_mod.f90 + EXO/exoplanet.f90 + src/cooling_h.f90), one block per
+    host thread along x; `scale` < 1 shrinks the grid for a bounded sample (same dx ratios, fewer cells)."""
+    import ctypes as C
+    from tests.oracle_lib import Oracle
+    from guacho_b200.exo import exo_params, Scalings
+    nx, ny, nz = (max(8, int(round(n * scale)) // 4 * 4) for n in (400, 100, 400))
+    threads = max(t for t in range(1, max(1, threads) + 1) if nx % t == 0 and nx // t >= 4)
+    p = exo_params(nx, ny, nz, MPI_NBX=threads)
+    sc = Scalings.of(p)
+    o = Oracle(p, fast=True, threads=threads)
+    o.L.orc_init_exo(o.h, *[C.c_double(v) for v in (sc.rsc, sc.rhosc, sc.Tempsc, sc.vsc2, sc.tsc, sc.bsc)])
+    o.L.orc_exo_initial_conditions(o.h)
+    o.start()
+    o.iter = 11
+    if warmup > 0:
+        o.run_timed(warmup)
+    sec = o.run_timed(steps)
+    zones = nx * ny * nz
+    sample = f"EXO {nx}x{ny}x{nz}" + (" (the shipped grid)" if scale == 1.0 else " (bounded sample of the shipped 400x100x400)") + f", {threads} blocks x 1 thread, {steps} steps after {warmup} warm-up"
+    return zones * steps / sec, sec / steps * 1e3, sample, threads
+
+
+EXO_METRIC = "MHD zone-updates/s (EXO as shipped: HLLD + flux-CD + 2 passives + EOS_H_RATE + COOL_H + wind-sphere BC + gravity source + eta, FP64)"
+EXO_WORKLOAD = "EXO/ exoplanet wind as shipped (BASELINE configs[3]): 400x100x400, HLLD MHD + flux-CD, 2 passives, EOS_H_RATE, COOL_H, outflow + user BC, gravity, eta 0.01, cfl 0.4"
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port: no Fortran compiler / MPI in this image)
     on the host cores, same workload, metric and unit; --steps / --warmup are honoured.  Rank 0 only."""
@@ -164,8 +191,16 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    p = workload(args.n, 1, False, args.solver)
     steps, warmup = max(1, args.steps), max(0, args.warmup)
+    if args.problem == "exo":
+        v, ms, sample, threads = exo_cpu_reference(steps, warmup, threads)
+        print(json.dumps({"impl": "reference", "metric": EXO_METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+                          "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": EXO_WORKLOAD, "sample": sample},
+                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return 0
+    p = workload(args.n, 1, False, args.solver)
     v, ms, sample, threads, full = cpu_reference(p, steps, warmup, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
@@ -177,6 +212,79 @@ def run_reference(args):
         "note": "reference is Fortran+MPI and cannot be built in this image (no Fortran compiler/MPI); this is the line-faithful C++ restatement in oracle/ "
                 "(ms_per_step is per step of the sampled grid; value is zone-updates/s and does not depend on the sample size)",
     }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_exo(args, rank, local_rank, world):
+    """BASELINE configs[3]: EXO as shipped on one GPU through the same C ABI (wind spheres, gravity, bc hook as device functors)."""
+    import torch
+    from guacho_b200.exo import Exo, exo_params
+    from guacho_b200.solver import Block
+    if world != 1:
+        raise SystemExit("--problem exo runs on one GPU (the shipped problem is 400x100x400)")
+    p = exo_params(strict_fp=args.strict, device=local_rank)
+    ex = Exo(p)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    with Block(p) as blk:
+        ex.attach(blk, 0.0)
+        u0 = ex.initial_conditions()
+        blk.set_state(u0)
+        tsim, it, _ = blk.run(max(3, args.warmup), 0.0, 1)
+        torch.cuda.synchronize()
+        l0, tw0 = blk.launch_count, time.time()
+        tsim, it, last_dt = blk.run(args.steps, tsim, it)
+        tw1, l1 = time.time(), blk.launch_count
+        ms = blk.last_elapsed_ms
+        clocks = sampler.stop(tw0, tw1)
+        zones = p.nx * p.ny * p.nz
+        value = zones * args.steps / (ms * 1e-3)
+        blk.set_profiling(True)
+        nprof = min(args.steps, 3)
+        tsim, it, _ = blk.run(nprof, tsim, it)
+        ktimes = blk.kernel_times()
+        blk.set_profiling(False)
+        # end to end: host buffers every step
+        e2e_steps = args.e2e_steps if args.e2e_steps is not None else 3
+        pinned = torch.empty(int(np.prod(p.block_shape())), dtype=torch.float64, pin_memory=True)
+        uh = pinned.numpy().reshape(p.block_shape(), order="F")
+        uh[...] = blk.get_state()
+        t_e, it_e = tsim, it
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            blk.set_time(t_e); blk.set_state(uh); dt, _d = blk.get_timestep(it_e, 10, t_e, 1e300); blk.tstep(dt); blk.get_state_into(uh); t_e += dt; it_e += 1
+        torch.cuda.synchronize()
+        e2e_sec = time.perf_counter() - t0
+        finite = bool(np.isfinite(uh).all())
+        fused = ktimes["stage2"][1] > 0
+    peak_gbs, peak_src = measured_peaks()
+    step_ms = ms / args.steps
+    bytes_zone = 40.0 * p.neq + 16.0 * p.neq          # 5*neq doubles + the eta pass (read up, write u): 400 + 160 B (SURVEY 8(d))
+    if fused:
+        dom_key, dom_name, dom_bytes = "stage2", "k_stage<HLLD,minmod,ORDER=2,fluxCD,2 passives,H_RATE,gravity>", 8.0 * (p.neq + (p.neq - 3) * 2 + 3)
+    else:
+        dom_key, dom_name, dom_bytes = "flux", "k_flux<HLLD,minmod> (pass-per-routine path: 3 launches per stage)", 2 * 8.0 * p.neq * 3
+    dom_ms = ktimes[dom_key][0] / nprof if ktimes[dom_key][1] else None
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, _ms, sample, threads = exo_cpu_reference(1, 1, os.cpu_count() or 1, scale=0.5)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+    line = {"metric": EXO_METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": EXO_WORKLOAD, "grid_total": [p.nxtot, p.nytot, p.nztot], "neq": p.neq, "path": "fused stage kernels" if fused else "pass-per-routine kernels",
+                       "kernels": "strict (-fmad=false)" if args.strict else "fast (-fmad=true)", "l2": "working set exceeds the 126 MB L2; no flush needed"},
+            "clocks": clocks,
+            "e2e": {"value": (zones * e2e_steps / e2e_sec if e2e_steps else None), "unit": UNIT, "h2d_bytes_per_step": int(uh.nbytes), "d2h_bytes_per_step": int(uh.nbytes) + 16,
+                    "steps": e2e_steps, "ms_per_step": (e2e_sec / e2e_steps * 1e3 if e2e_steps else None)},
+            "gpu_launches": int(l1 - l0),
+            "roofline": {"bound": "hbm", "achieved": (dom_bytes * zones / (dom_ms * 1e-3) / 1e9 if dom_ms else None), "peak": peak_gbs, "unit": "GB/s",
+                         "frac": (dom_bytes * zones / (dom_ms * 1e-3) / 1e9 / peak_gbs if dom_ms else None), "traffic": None, "peak_source": peak_src, "kernel": dom_name,
+                         "ms_per_step": dom_ms, "algorithmic_bytes_per_zone": dom_bytes,
+                         "whole_step": {"achieved": bytes_zone * zones / (step_ms * 1e-3) / 1e9, "frac": bytes_zone * zones / (step_ms * 1e-3) / 1e9 / peak_gbs,
+                                        "algorithmic_bytes_per_zone": bytes_zone, "definition": "40*neq + 16*neq B per zone-update (eta != 0: extra up -> u pass), neq = 10"},
+                         "kernel_ms_per_step": {k: v[0] / nprof for k, v in ktimes.items() if v[1]}},
+            "cpu_baseline": cpu, "finite": finite, "last_dt": last_dt}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -193,6 +301,7 @@ def main():
     ap.add_argument("--strict", action="store_true", help="use the -fmad=false bit-comparison kernels")
     ap.add_argument("--solver", default="hlld", choices=sorted(SOLVERS), help="Riemann solver (BASELINE configs[4] sweep); the headline metric is hlld")
     ap.add_argument("--strong", action="store_true", help="strong scaling: --n is the TOTAL grid side, split into z-slabs over the GPUs")
+    ap.add_argument("--problem", default="ot", choices=["ot", "exo"], help="ot: the headline workload; exo: EXO/ as shipped (BASELINE configs[3]), 400x100x400, one GPU")
     ap.add_argument("--no-extras", action="store_true", help="skip the 512^3 lines (extra.grid512 at N=1; extra.weak512 / extra.strong512 at N>1)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -211,6 +320,8 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
 
+    if args.problem == "exo":
+        return run_exo(args, rank, local_rank, world)
     if args.strong and args.n % world:
         raise SystemExit(f"--strong: {args.n} planes do not split over {world} GPUs")
     p = workload(args.n, world, args.strong, args.solver).replace(strict_fp=args.strict)

@@ -76,7 +76,7 @@ struct gx_solver {
   cudaStream_t cstream = nullptr;                             // halo push stream (overlaps the interior launches)
   cudaEvent_t ev_bnd = nullptr, ev_comm = nullptr;
   bool overlap = false;                                       // z slabs + peer push: boundary-first launches, exchange on cstream
-  double *U = nullptr, *UP = nullptr, *W = nullptr, *F = nullptr, *E = nullptr, *Temp = nullptr;
+  double *U = nullptr, *UP = nullptr, *W = nullptr, *F = nullptr, *E = nullptr, *Temp = nullptr, *T = nullptr;
   double* stage = nullptr; size_t stage_doubles = 0;         // AoS staging for layout conversion
   double* halo_send[6] = {0, 0, 0, 0, 0, 0};                  // packed faces (multi-GPU)
   double* halo_recv[6] = {0, 0, 0, 0, 0, 0};
@@ -84,6 +84,7 @@ struct gx_solver {
   struct DevScalars { unsigned long long dtmin_bits; int err; int pad; }* dscal = nullptr;   // device
   DevScalars* hscal = nullptr;                                // pinned host mirror
   bool have_state = false;
+  bool fills_by_caller = false;   // overlapped step: it launches the periodic x / y fills itself (boundary planes first)
   bool ghosts_stale = false;   // self-periodic ghost layers of u/up not materialised since the last fused step
   bool fused = false;      // fused stage kernels (gx_stage.cu); otherwise the pass-per-routine kernels
   int kz = 0;              // planes one CTA of the fused stage kernel marches through (0: the launcher fills whole waves of SMs; GX_KZ overrides)
@@ -185,6 +186,34 @@ __global__ void k_bc_face(Grid g, int nvar, double* __restrict__ A, int dir, int
   }
 }
 
+// Periodic ghost layers of a block that is its own neighbour in x / y, planes k0..k1 (Fortran k), for the arrays the TMA loaders
+// of the fused stage kernels read (they cannot wrap an index).  Same copies as k_bc_face mode 0, laid out for the memory system:
+//   x: one thread per (row, plane, variable, side) moves the nl cells of that row end (a 16-byte pair for nl = 2: both ends of a
+//      row sit on even elements) — rows j = 1..ny; the corner columns come from the y pass, which runs second over i = 1-nl..nx+nl;
+//   y: one thread per cell of a ghost row, x fastest: whole rows, coalesced.
+__global__ void __launch_bounds__(128) k_fill_x_periodic(Grid g, int nvar, double* __restrict__ A, int nl, int k0) {
+  const int j = (int)(blockIdx.x * blockDim.x + threadIdx.x) + 1;
+  if (j > g.ny) return;
+  const int k = (int)blockIdx.y + k0;
+  const int q = (int)blockIdx.z >> 1, side = (int)blockIdx.z & 1;
+  double* row = A + (long long)q * g.vs + g.idx(0, j, k);          // element of Fortran i = 0
+  if (nl == 2) {
+    if (side == 0) *reinterpret_cast<double2*>(row - 1) = *reinterpret_cast<const double2*>(row + g.nx - 1);       // i = -1, 0 <- nx-1, nx
+    else *reinterpret_cast<double2*>(row + g.nx + 1) = *reinterpret_cast<const double2*>(row + 1);                 // i = nx+1, nx+2 <- 1, 2
+  } else {
+    if (side == 0) row[0] = row[g.nx];
+    else row[g.nx + 1] = row[1];
+  }
+}
+__global__ void __launch_bounds__(128) k_fill_y_periodic(Grid g, int nvar, double* __restrict__ A, int nl, int k0) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) + 1 - nl;
+  if (i > g.nx + nl) return;
+  const int k = (int)blockIdx.y + k0;
+  const int q = (int)blockIdx.z / (2 * nl), r = (int)blockIdx.z - q * 2 * nl, side = r / nl, l = r - side * nl;
+  const int jd = side == 0 ? 1 - nl + l : g.ny + 1 + l, js = side == 0 ? jd + g.ny : jd - g.ny;
+  A[(long long)q * g.vs + g.idx(i, jd, k)] = A[(long long)q * g.vs + g.idx(i, js, k)];
+}
+
 // pack / unpack a box [lo,hi] (Fortran indices, inclusive) of nvar variables to/from a contiguous buffer
 struct Box { int lo[3], hi[3]; };
 __global__ void k_pack(Grid g, int nvar, double* A, double* buf, Box bx, int unpack_flag) {
@@ -203,42 +232,56 @@ __global__ void k_pack(Grid g, int nvar, double* A, double* buf, Box bx, int unp
 
 // impose_user_bc functor: wind spheres (EXO/exoplanet.f90:125-266).  First matching sphere wins
 // (the reference tests the star first, then `else if` the planet).
-struct WindSpheres { int n; gx_wind_sphere s[GX_MAX_SPHERES]; };
-__global__ void k_wind_spheres(Grid g, gxp::Phys P, int mhd, const WindSpheres WS, double* __restrict__ A) {
-  const gx_wind_sphere* sph = WS.s; const int nsph = WS.n;
-  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) - 1;
-  const int j = (int)blockIdx.y - 1, k = (int)blockIdx.z - 1;
-  if (i > g.nx + 2) return;
+// One launch per sphere over the sphere's bounding box (clipped to the block with its ghost cells); the spheres are applied LAST to
+// FIRST, so where two overlap the earlier one ends up in the cells — the reference's `if star ... else if planet`.
+__global__ void k_wind_sphere(Grid g, gxp::Phys P, int mhd, const gx_wind_sphere S, double* __restrict__ A, int ilo, int jlo, int klo, int ihi) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) + ilo;
+  const int j = (int)blockIdx.y + jlo, k = (int)blockIdx.z + klo;
+  if (i > ihi) return;
   const double x = ((double)(i + g.cx * g.nx - g.nxtot / 2) + 0.5) * g.dx;
   const double y = ((double)(j + g.cy * g.ny - g.nytot / 2) + 0.5) * g.dy;
   const double z = ((double)(k + g.cz * g.nz - g.nztot / 2) + 0.5) * g.dz;
   const long long c = g.idx(i, j, k);
-  for (int m = 0; m < nsph; ++m) {
-    const gx_wind_sphere& S = sph[m];
-    const double xl = x - S.xc, yl = y - S.yc, zl = z - S.zc;
-    double rad = sqrt(xl * xl + yl * yl + zl * zl);
-    if (rad <= S.radius) {
-      if (rad == 0.) rad = g.dx * 0.10;
-      const double velx = S.vbx + S.vwind * xl / rad, vely = S.vby + S.vwind * yl / rad, velz = S.vbz + S.vwind * zl / rad;
-      const double dens = S.dens;
-      A[0 * g.vs + c] = dens;
-      A[1 * g.vs + c] = dens * velx;
-      A[2 * g.vs + c] = dens * vely;
-      A[3 * g.vs + c] = dens * velz;
-      double b2h = 0.0;
-      if (g.neqdyn == 8) {
-        const double q3 = S.radius / rad;
-        const double cpi = S.bdip * (q3 * q3 * q3) / (2. * (rad * rad));
-        const double bx = 3. * yl * xl * cpi, by = (3. * (yl * yl) - rad * rad) * cpi, bz = 3. * yl * zl * cpi;
-        A[5 * g.vs + c] = bx; A[6 * g.vs + c] = by; A[7 * g.vs + c] = bz;
-        b2h = 0.5 * (bx * bx + by * by + bz * bz);
-      }
-      double e = 0.5 * dens * (velx * velx + vely * vely + velz * velz) + P.cv * dens * S.tfac * S.temp;   // exoplanet.f90:181-188,236-243
-      if (mhd) e = e + b2h;
-      A[4 * g.vs + c] = e;
-      for (int q = 0; q < g.npas && q < 4; ++q) A[(long long)(g.neqdyn + q) * g.vs + c] = S.pas[q] * dens;
-      return;
+  const double xl = x - S.xc, yl = y - S.yc, zl = z - S.zc;
+  double rad = sqrt(xl * xl + yl * yl + zl * zl);
+  if (rad <= S.radius) {
+    if (rad == 0.) rad = g.dx * 0.10;
+    const double velx = S.vbx + S.vwind * xl / rad, vely = S.vby + S.vwind * yl / rad, velz = S.vbz + S.vwind * zl / rad;
+    const double dens = S.dens;
+    A[0 * g.vs + c] = dens;
+    A[1 * g.vs + c] = dens * velx;
+    A[2 * g.vs + c] = dens * vely;
+    A[3 * g.vs + c] = dens * velz;
+    double b2h = 0.0;
+    if (g.neqdyn == 8) {
+      const double q3 = S.radius / rad;
+      const double cpi = S.bdip * (q3 * q3 * q3) / (2. * (rad * rad));
+      const double bx = 3. * yl * xl * cpi, by = (3. * (yl * yl) - rad * rad) * cpi, bz = 3. * yl * zl * cpi;
+      A[5 * g.vs + c] = bx; A[6 * g.vs + c] = by; A[7 * g.vs + c] = bz;
+      b2h = 0.5 * (bx * bx + by * by + bz * bz);
     }
+    double e = 0.5 * dens * (velx * velx + vely * vely + velz * velz) + P.cv * dens * S.tfac * S.temp;   // exoplanet.f90:181-188,236-243
+    if (mhd) e = e + b2h;
+    A[4 * g.vs + c] = e;
+    for (int q = 0; q < g.npas && q < 4; ++q) A[(long long)(g.neqdyn + q) * g.vs + c] = S.pas[q] * dens;
+  }
+}
+static void launch_wind_spheres(gx_solver* s, double* A) {
+  const Grid& g = s->A.g;
+  for (int m = (int)s->spheres.size() - 1; m >= 0; --m) {
+    const gx_wind_sphere& S = s->spheres[m];
+    // cell i has x = (i + cx*nx - nxtot/2 + 0.5) dx: indices whose centre can lie within radius (+1 cell of slack), clipped to -1 .. n+2
+    auto range = [](double c, double r, double d, int off, int n, int& lo, int& hi) {
+      lo = std::max(-1, (int)floor((c - r) / d - 0.5) - off - 1);
+      hi = std::min(n + 2, (int)ceil((c + r) / d - 0.5) - off + 1);
+    };
+    int ilo, ihi, jlo, jhi, klo, khi;
+    range(S.xc, S.radius, g.dx, g.cx * g.nx - g.nxtot / 2, g.nx, ilo, ihi);
+    range(S.yc, S.radius, g.dy, g.cy * g.ny - g.nytot / 2, g.ny, jlo, jhi);
+    range(S.zc, S.radius, g.dz, g.cz * g.nz - g.nztot / 2, g.nz, klo, khi);
+    if (ilo > ihi || jlo > jhi || klo > khi) continue;
+    LaunchScope ls(s, gx::KC_BC);
+    k_wind_sphere<<<dim3((ihi - ilo + 1 + 63) / 64, jhi - jlo + 1, khi - klo + 1), 64, 0, s->stream>>>(g, s->A.phys, s->cfg.mhd, S, A, ilo, jlo, klo, ihi);
   }
 }
 
@@ -480,6 +523,20 @@ static void launch_bc_face(gx_solver* s, double* A, int nvar, int dir, int side,
   k_bc_face<<<grid, 64, 0, s->stream>>>(g, nvar, A, dir, side, mode, nl, negvar);
 }
 
+// x / y periodic ghost layers of planes k0..k1 with the lean kernels (only self-periodic directions; see k_fill_x_periodic)
+static void fill_xy_periodic(gx_solver* s, double* A, int nvar, int nl, int k0, int k1, cudaStream_t st) {
+  const Grid& g = s->A.g;
+  if (k1 < k0) return;
+  if (s->nb[0] == 1 && s->periodic[0]) {
+    LaunchScope ls(s, gx::KC_BC);
+    k_fill_x_periodic<<<dim3((g.ny + 127) / 128, k1 - k0 + 1, 2 * nvar), 128, 0, st>>>(g, nvar, A, nl, k0);
+  }
+  if (s->nb[1] == 1 && s->periodic[1]) {
+    LaunchScope ls(s, gx::KC_BC);
+    k_fill_y_periodic<<<dim3((g.nx + 2 * nl + 127) / 128, k1 - k0 + 1, 2 * nl * nvar), 128, 0, st>>>(g, nvar, A, nl, k0);
+  }
+}
+
 // kind 0: conserved/primitive array (closed wall flips normal momentum, boundaries.f90:146-199, 361-438)
 // kind 1: electric field (closed wall flips e(1) on x walls, e(2) on y walls, nothing on z walls,
 //         flux_cd_module.f90:143-192)
@@ -489,6 +546,9 @@ static void launch_bc_face(gx_solver* s, double* A, int nvar, int dir, int side,
 // download entry points use, so that gx_get_state / gx_get_up are NOT collective calls.
 static int apply_boundaries(gx_solver* s, double* A, int nvar, int nl, int kind, bool skip_wrapped = false, cudaStream_t st = nullptr,
                             bool local_only = false) {
+  // ... except the stage loaders in x and y when they read ghost cells as they are (TMA): u / up keep those layers current
+  // (the overlapped step places these fills itself, around its boundary-first launches)
+  if (skip_wrapped && kind == 0 && s->A.ldghost && !s->fills_by_caller) fill_xy_periodic(s, A, nvar, nl, 1, s->A.g.nz, st ? st : s->stream);
   for (int dir = 0; dir < 3; ++dir) {
     if (s->nb[dir] == 1 && s->periodic[dir]) {            // neighbour is the block itself
       if (skip_wrapped && s->A.wrap[dir]) continue;       // the fused kernels wrap their reads instead
@@ -521,12 +581,7 @@ static int apply_user_bc(gx_solver* s, double* A, int order) {
   // the reference's impose_user_bc is also where problem modules move their state (the orbiting planet,
   // EXO/exoplanet.f90:137-144): the host hook may re-position the device functors before they are applied
   if (s->bc_hook) s->bc_hook(order, s->time, s->bc_hook_user);
-  if (!s->spheres.empty()) {
-    LaunchScope ls(s, gx::KC_BC);
-    WindSpheres WS; WS.n = (int)s->spheres.size();
-    for (int m = 0; m < WS.n; ++m) WS.s[m] = s->spheres[m];
-    k_wind_spheres<<<dim3((g.nx + 4 + 127) / 128, g.ny + 4, g.nz + 4), 128, 0, s->stream>>>(g, s->A.phys, s->cfg.mhd, WS, A);
-  }
+  if (!s->spheres.empty()) launch_wind_spheres(s, A);
   if (s->host_bc) {   // slow path: device -> host -> callback -> device
     std::vector<double> h((size_t)g.neq * (g.nx + 4) * (g.ny + 4) * (g.nz + 4));
     int rc = download_aos(s, A, h.data(), g.neq); if (rc) return rc;
@@ -576,7 +631,7 @@ int gx_riemann_flux(const gx_config* c, int32_t n, const double* wl, const doubl
   if (c->device >= 0) { if (c->device >= ndev) return fail(GX_ENODEVICE, "device %d of %d", c->device, ndev); cudaSetDevice(c->device); }
   if (n == 0) return GX_OK;
   gxp::Phys P{};
-  P.cv = c->cv; P.gamma = c->gamma; P.Tempsc = c->Tempsc; P.inv_cv = 1.0 / c->cv; P.m4gamma = -4.0 * c->gamma;
+  P.cv = c->cv; P.gamma = c->gamma; P.Tempsc = c->Tempsc; P.inv_cv = 1.0 / c->cv; P.m4gamma = -4.0 * c->gamma; P.inv_Tempsc = 1.0 / c->Tempsc;
   P.eos = c->eq_of_state; P.neqdyn = c->neqdyn; P.npas = 0;
   const int nq = c->neqdyn;
   std::vector<double> hl((size_t)n * 8, 0.0), hr((size_t)n * 8, 0.0), hf((size_t)n * 8, 0.0);
@@ -649,7 +704,7 @@ int gx_create(const gx_config* c, gx_solver** out) {
   g.cx = c->cx; g.cy = c->cy; g.cz = c->cz;
   g.nxtot = c->nxtot; g.nytot = c->nytot; g.nztot = c->nztot;
   g.dx = c->dx; g.dy = c->dy; g.dz = c->dz;
-  s->A.phys.cv = c->cv; s->A.phys.gamma = c->gamma; s->A.phys.Tempsc = c->Tempsc; s->A.phys.inv_cv = 1.0 / c->cv; s->A.phys.m4gamma = -4.0 * c->gamma;
+  s->A.phys.cv = c->cv; s->A.phys.gamma = c->gamma; s->A.phys.Tempsc = c->Tempsc; s->A.phys.inv_cv = 1.0 / c->cv; s->A.phys.m4gamma = -4.0 * c->gamma; s->A.phys.inv_Tempsc = 1.0 / c->Tempsc;
   s->A.phys.eos = c->eq_of_state; s->A.phys.neqdyn = c->neqdyn; s->A.phys.npas = c->npas;
   s->A.idx3[0] = 1.0 / c->dx; s->A.idx3[1] = 1.0 / c->dy; s->A.idx3[2] = 1.0 / c->dz;
   s->A.solver = c->riemann_solver; s->A.limiter = c->slope_limiter;
@@ -674,18 +729,29 @@ int gx_create(const gx_config* c, gx_solver** out) {
 #define ALLOC(p, n) do { cudaError_t e_ = cudaMalloc((void**)&(p), (n)); if (e_ != cudaSuccess) { std::string m = cudaGetErrorString(e_); gx_destroy(s); return fail(GX_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", (size_t)(n), m.c_str()); } cudaMemsetAsync((p), 0, (n), 0); } while (0)
   if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { s->stream = nullptr; gx_destroy(s); cudaGetLastError(); return fail(GX_ECUDA, "cudaStreamCreate failed"); }
   const size_t var_bytes = (size_t)g.vs * sizeof(double);
-  // fused stage kernels cover the dynamic variables with the adiabatic equation of state; passives, the 8-wave / user sources and
-  // eta != 0 (viscous_copy needs up's stale half-step ghosts) take the pass-per-routine kernels
-  s->fused = c->npas == 0 && !c->eight_wave && !c->user_source_terms && c->eta == 0.0 && c->eq_of_state == GX_EOS_ADIABATIC && !getenv("GX_NO_FUSED");
+  // Fused stage kernels (gx_stage.cu): (a) the dynamic variables with the adiabatic equation of state, no sources — the headline path;
+  // (b) two passive scalars, any equation of state but EOS_CHEM, user sources as the point-mass gravity functor — EXO as shipped.
+  // eta != 0 adds the viscous_copy pass (its stale half-step ghosts are reproduced).  The 8-wave source, other passive
+  // counts and a host-callback source (gx_register_host_source switches this off) take the pass-per-routine kernels.
+  const bool fuse_a = c->npas == 0 && !c->user_source_terms && c->eq_of_state == GX_EOS_ADIABATIC;
+  const bool fuse_b = c->npas == 2;
+  s->fused = (fuse_a || fuse_b) && !c->eight_wave && !getenv("GX_NO_FUSED");
   s->kz = 0;                                        // planes per CTA of the fused stage kernels: chosen by their launcher
   if (const char* e = getenv("GX_KZ")) s->kz = std::max(1, atoi(e));
   // a user boundary functor may write ghost cells, so ghosts must be real arrays then
   for (int d = 0; d < 3; ++d) s->A.wrap[d] = (s->fused && s->periodic[d] && s->nb[d] == 1 && !c->bc_user && !getenv("GX_NO_WRAP")) ? 1 : 0;
+  // The loaders of the fused headline kernels are ONE TMA tile load per plane (GX_TMA=0: per-thread cp.async).  TMA reads ghost cells
+  // as they are, so where x / y are self-periodic their ghost layers of u / up are kept current by the lean fill kernels
+  // (fill_xy_periodic) instead of being wrapped in the loaders; z still wraps through the box coordinate.
+  s->A.tma = (fuse_a && s->fused && !(getenv("GX_TMA") && !atoi(getenv("GX_TMA")))) ? 1 : 0;
+  s->A.ldghost = (s->A.tma && (s->A.wrap[0] || s->A.wrap[1])) ? 1 : 0;
   ALLOC(s->U, var_bytes * g.neq);
   ALLOC(s->UP, var_bytes * g.neq);
   if (!s->fused) {                                   // primitives and face fluxes only exist in HBM on the unfused path
     ALLOC(s->W, var_bytes * g.neq);
     ALLOC(s->F, var_bytes * g.neq * 3);
+  } else if (c->eta != 0.0) {
+    ALLOC(s->T, var_bytes * g.neq);                  // full-step state before viscous_copy (up keeps its half-step ghosts)
   }
   if (c->enable_flux_cd) ALLOC(s->E, var_bytes * 3);
   ALLOC(s->dscal, sizeof(gx_solver::DevScalars));
@@ -728,7 +794,7 @@ int gx_destroy(gx_solver* s) {
   }
   if (s->flags) cudaFree(s->flags);
   if (s->comm && g_nccl.ok) g_nccl.CommDestroy(s->comm);
-  double* ptrs[] = {s->U, s->UP, s->W, s->F, s->E, s->Temp, s->stage};
+  double* ptrs[] = {s->U, s->UP, s->W, s->F, s->E, s->Temp, s->T, s->stage};
   for (double* p : ptrs) if (p) cudaFree(p);
   for (int q = 0; q < 6; ++q) { if (s->halo_send[q]) cudaFree(s->halo_send[q]); if (s->halo_recv[q]) cudaFree(s->halo_recv[q]); }
   if (s->dscal) cudaFree(s->dscal);
@@ -826,14 +892,21 @@ static int tstep_enqueue_fused(gx_solver* s, double dt_cfl) {
   rc = apply_boundaries(s, s->UP, neq, 2, 0, true); if (rc) return rc;          // boundaryII :169
   rc = apply_user_bc(s, s->UP, 2); if (rc) return rc;
   rc = reset_dtmin(s); if (rc) return rc;
-  { LaunchScope ls(s, gx::KC_STAGE2); rc = K->stage(A, 2, dt_cfl, s->UP, s->U, s->U, s->E, s->kz, &s->dscal->dtmin_bits, cfl_in_step && !A.flux_cd, &s->dscal->err, s->stream); } if (rc) return fail(rc, "stage-2 launch");
+  // eta == 0: viscous_copy is u(interior) = up(interior), so the full step goes straight into u.  eta != 0: it goes into T and
+  // viscous_copy (hydro_solver.f90:54-63) reads T inside the block and up — the half-step halo of boundaryII — in the ghost cells
+  const bool visc = s->cfg.eta != 0.0;
+  const bool cfl2 = cfl_in_step && !visc && s->cfg.cooling == GX_COOL_NONE;   // nothing may touch u after the stage for its CFL to stand
+  double* full = visc ? s->T : s->U;
+  { LaunchScope ls(s, gx::KC_STAGE2); rc = K->stage(A, 2, dt_cfl, s->UP, s->U, full, s->E, s->kz, &s->dscal->dtmin_bits, cfl2 && !A.flux_cd, &s->dscal->err, s->stream); } if (rc) return fail(rc, "stage-2 launch");
   if (A.flux_cd) {
     rc = apply_boundaries(s, s->E, 3, 1, 1, true); if (rc) return rc;
-    { LaunchScope ls(s, gx::KC_BUPDATE); K->bupdate(A, dt_cfl, s->U, s->E, s->U, &s->dscal->dtmin_bits, cfl_in_step, s->stream); }
+    { LaunchScope ls(s, gx::KC_BUPDATE); K->bupdate(A, dt_cfl, s->U, s->E, full, &s->dscal->dtmin_bits, cfl2, s->stream); }
   }
+  if (visc) { LaunchScope ls(s, gx::KC_VISC); K->viscous2(A, s->cfg.eta, s->T, s->UP, s->U, s->stream); }               // :188
+  if (s->cfg.cooling == GX_COOL_H) launch_coolingh(s, dt_cfl);                  // coolingh :202-204
   rc = apply_boundaries(s, s->U, neq, 1, 0, true); if (rc) return rc;           // boundaryI :216
   rc = apply_user_bc(s, s->U, 1); if (rc) return rc;
-  if (!cfl_in_step) {
+  if (!cfl2) {
     LaunchScope ls(s, gx::KC_PRIM);
     K->calcprim(A, s->U, nullptr, nullptr, &s->dscal->dtmin_bits, 1, s->stream);
   }
@@ -872,9 +945,17 @@ static int tstep_enqueue_fused_overlap(gx_solver* s, double dt_cfl) {
   };
   auto bupdate = [&](double dt, const double* Ub, double* dst, int nl, unsigned long long* dtmin, int want_cfl) -> int {
     for (const StepArgs* a : {&blo, &bhi}) { LaunchScope ls(s, gx::KC_BUPDATE); K->bupdate(*a, dt, Ub, s->E, dst, dtmin, want_cfl, s->stream); }
+    if (s->A.ldghost) {       // the planes that travel carry their own periodic x / y ghost layers (the neighbour's loader reads them)
+      fill_xy_periodic(s, dst, neq, nl, 1, 2, s->stream);
+      fill_xy_periodic(s, dst, neq, nl, nz - 1, nz, s->stream);
+    }
     fork();
-    int r = apply_boundaries(s, dst, neq, nl, 0, true, s->cstream); if (r) return r;    // boundaryII (nl = 2) / boundaryI (nl = 1)
+    s->fills_by_caller = true;
+    int r = apply_boundaries(s, dst, neq, nl, 0, true, s->cstream);                     // boundaryII (nl = 2) / boundaryI (nl = 1)
+    s->fills_by_caller = false;
+    if (r) return r;
     { LaunchScope ls(s, gx::KC_BUPDATE); K->bupdate(bmid, dt, Ub, s->E, dst, dtmin, want_cfl, s->stream); }
+    if (s->A.ldghost) fill_xy_periodic(s, dst, neq, nl, 3, nz - 2, s->stream);
     join();
     return GX_OK;
   };
@@ -889,7 +970,7 @@ static int tstep_enqueue_fused_overlap(gx_solver* s, double dt_cfl) {
 }
 
 static int tstep_enqueue(gx_solver* s, double dt_cfl) {
-  if (s->fused && s->overlap) return tstep_enqueue_fused_overlap(s, dt_cfl);
+  if (s->fused && s->overlap && s->cfg.eta == 0.0 && s->cfg.cooling == GX_COOL_NONE && !s->cfg.bc_user) return tstep_enqueue_fused_overlap(s, dt_cfl);
   if (s->fused) return tstep_enqueue_fused(s, dt_cfl);
   const gx::KernelTable* K = s->K;
   const StepArgs& A = s->A;
@@ -1008,7 +1089,15 @@ int gx_get_up(gx_solver* s, double* up) {
 
 int gx_register_host_source(gx_solver* s, gx_host_source_fn cb, void* user) {
   if (!s) return fail(GX_EINVAL, "null argument");
-  if (cb && !s->cfg.user_source_terms) return fail(GX_EINVAL, "gx_register_host_source needs user_source_terms = 1 (the fused kernels carry no source terms)");
+  if (cb && !s->cfg.user_source_terms) return fail(GX_EINVAL, "gx_register_host_source needs user_source_terms = 1");
+  if (cb && s->fused) {          // a host callback needs the primitives in HBM: leave the fused kernels for the pass-per-routine path
+    if (s->have_state) return fail(GX_ESTATE, "gx_register_host_source must be called before gx_set_state");
+    cudaSetDevice(s->device);
+    s->fused = false;
+    for (int d = 0; d < 3; ++d) s->A.wrap[d] = 0;
+    int rc = ensure_array(s, &s->W, s->A.g.neq); if (rc) return rc;
+    rc = ensure_array(s, &s->F, (size_t)s->A.g.neq * 3); if (rc) return rc;
+  }
   s->host_src = cb; s->host_src_user = user;
   return GX_OK;
 }

@@ -218,6 +218,23 @@ __global__ void __launch_bounds__(128) k_viscous(const StepArgs A, double eta, c
   }
 }
 
+// viscous_copy when the full-step state was written to T instead of up (fused path): the reference reads up(i+-1, ...) whose ghost
+// cells still hold the half-step halo of boundaryII — a neighbour outside the block is therefore read from UP
+__global__ void __launch_bounds__(128) k_viscous2(const StepArgs A, double eta, const double* __restrict__ T, const double* __restrict__ UP, double* __restrict__ U) {
+  const Grid& g = A.g;
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) + 1, j = (int)blockIdx.y + 1, k = (int)blockIdx.z + 1;
+  if (i > g.nx) return;
+  const long long c = g.idx(i, j, k), sy = g.px, sz = (long long)g.px * g.py;
+  for (int q = 0; q < g.neq; ++q) {
+    const double* p = T + q * g.vs + c;
+    const double* h = UP + q * g.vs + c;
+    const double xp = i < g.nx ? p[1] : h[1], xm = i > 1 ? p[-1] : h[-1];
+    const double yp = j < g.ny ? p[sy] : h[sy], ym = j > 1 ? p[-sy] : h[-sy];
+    const double zp = k < g.nz ? p[sz] : h[sz], zm = k > 1 ? p[-sz] : h[-sz];
+    U[q * g.vs + c] = p[0] + eta * (xp + xm + yp + ym + zp + zm - 6. * p[0]);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // flux-CD evolution of B from the cell-centred E (flux_cd_update, src/flux_cd_module.f90:311-321),
 // the companion of the fused stage kernel; with want_cfl also the CFL candidates of the
@@ -258,7 +275,7 @@ __global__ void __launch_bounds__(32 * GX_BU_Y * GX_BU_Z) k_bupdate(const StepAr
 #pragma unroll
       for (int q = 0; q < 5; ++q) u[q] = dst[q * vs + c];
       u[5] = bx; u[6] = by; u[7] = bz;
-      gxp::u2prim<true>(A.phys, u, w, 0.0, T);
+      gxp::u2prim<true>(A.phys, u, w, g.npas > 0 ? dst[8 * vs + c] : 0.0, T);    // EOS_H_RATE reads the first passive
       double cx, cy, cz;
       gxp::cfast3(A.phys, w[4], w[0], w[5], w[6], w[7], cx, cy, cz);
 #if defined(GX_FLAVOUR_FAST)
@@ -371,6 +388,11 @@ static void l_viscous(const StepArgs& A, double eta, const double* UP, double* U
   k_viscous<<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(A, eta, UP, U);
 }
 
+static void l_viscous2(const StepArgs& A, double eta, const double* T, const double* UP, double* U, cudaStream_t s) {
+  const Grid& g = A.g;
+  k_viscous2<<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(A, eta, T, UP, U);
+}
+
 // fused stage kernels live in gx_stage.cu, one translation unit per solver
 int l_stage_1(const StepArgs&, int, double, const double*, const double*, double*, double*, int, unsigned long long*, int, int*, cudaStream_t);
 int l_stage_2(const StepArgs&, int, double, const double*, const double*, double*, double*, int, unsigned long long*, int, int*, cudaStream_t);
@@ -395,7 +417,7 @@ static void l_bupdate(const StepArgs& A, double dt, const double* Ub, const doub
   else k_bupdate<false><<<grid, block, 0, s>>>(A, dt, Ub, E, dst, dtmin_bits);
 }
 
-static const KernelTable table = {l_calcprim, l_fluxes, l_efield, l_update, l_viscous, l_stage, l_bupdate, l_riemann_points};
+static const KernelTable table = {l_calcprim, l_fluxes, l_efield, l_update, l_viscous, l_viscous2, l_stage, l_bupdate, l_riemann_points};
 
 }  // namespace GX_NS
 

@@ -36,6 +36,9 @@ struct StepArgs {
   int wrap[3];             // direction is periodic with the block as its own neighbour: the fused
                            // kernels read the wrapped cell instead of a ghost cell (ghosts are
                            // then only materialised when the host asks for the arrays)
+  int tma;                 // stage the planes of the fused stage kernels with TMA tile loads (one per plane) instead of per-thread cp.async
+  int ldghost;             // the stage loaders read the x / y ghost cells of u / up as they are (TMA cannot wrap an index): those layers are
+                           // kept current by the periodic fill kernels; wrap[] then only steers the E stencil of the flux-CD update and z
   int kbeg, klast;         // planes (Fortran k) the fused stage / B-update launch covers; 1..nz unless the step is split into
                            // boundary-first and interior launches to overlap the halo exchange (multi-GPU)
   gxp::Phys phys;
@@ -58,6 +61,8 @@ struct KernelTable {
   // dst = U - dt*div(F) [flux-CD for B] [+ dt*S(W)]
   void (*update)(const StepArgs&, double dt, const double* U, const double* F, const double* E, const double* W, double* dst, cudaStream_t);
   void (*viscous)(const StepArgs&, double eta, const double* UP, double* U, cudaStream_t);
+  // viscous_copy of the fused path: the full-step state lives in T (physical cells), the ghost cells it reads are up's
+  void (*viscous2)(const StepArgs&, double eta, const double* T, const double* UP, double* U, cudaStream_t);
   // fused stage (gx_stage.cu): dst = Ub - dt*div F(prim(S)) for the non-B variables (all variables
   // without flux-CD), E = cell-centred electric field of the same fluxes (flux-CD only);
   // without flux-CD and with want_cfl the CFL minimum of the new state goes to *dtmin_bits.

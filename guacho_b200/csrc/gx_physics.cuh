@@ -18,6 +18,7 @@ struct Phys {            // the scalar `parameter`s the cell routines read
   double cv, gamma, Tempsc;
   double inv_cv;         // 1/cv (fast build: p = (...)*inv_cv instead of an IEEE division)
   double m4gamma;        // -4 gamma (fast build: discriminant of the fast speed)
+  double inv_Tempsc;     // 1/Tempsc (fast build: pressure from the floored temperature)
   int eos;               // GX_EOS_*
   int neqdyn, npas;      // neq = neqdyn + npas
 };
@@ -138,12 +139,22 @@ __device__ __forceinline__ void u2prim(const Phys& P, const double (&u)[8], doub
     if (WANT_T) T = (p / r) * P.Tempsc;
   } else if (P.eos == GX_EOS_SINGLE_SPECIE) {
     double rr = gx_max(r, 1e-15);
+#if defined(GX_FLAVOUR_FAST)
+    T = gx_max(1.0, (p * dr.inv) * P.Tempsc);          // rr == r (already floored)
+    p = rr * T * P.inv_Tempsc;
+#else
     T = gx_max(1.0, (p / rr) * P.Tempsc);
     p = rr * T / P.Tempsc;
+#endif
   } else if (P.eos == GX_EOS_H_RATE && P.npas > 0) {
     double dentot = gx_max(2.0 * r - pas0, 1e-15);
+#if defined(GX_FLAVOUR_FAST)
+    T = gx_max(1.0, (p * fast_rcp(dentot)) * P.Tempsc);
+    p = dentot * T * P.inv_Tempsc;
+#else
     T = gx_max(1.0, (p / dentot) * P.Tempsc);
     p = dentot * T / P.Tempsc;
+#endif
   }
   w[4] = p;
 }
@@ -328,6 +339,22 @@ struct PasInfo {
   int mode;
   double ul, ur, sl, sr, a, b, c;   // meaning depends on mode
 };
+#if defined(GX_FLAVOUR_FAST)
+// Every closed form below is linear in (ql, qr): flux = cl*ql + cr*qr with coefficients that depend on the interface only.
+// The production build forms them once per interface (one reciprocal) instead of dividing per passive scalar.
+__device__ __forceinline__ void passive_coeffs(const PasInfo& I, double& cl, double& cr) {
+  cl = 0.0; cr = 0.0;
+  switch (I.mode) {
+    case PAS_UPL: cl = I.ul; break;
+    case PAS_UPR: cr = I.ur; break;
+    case PAS_HLL: { const double r = fast_rcp(I.sr - I.sl), ss = I.sl * I.sr; cl = (I.sr * I.ul - ss) * r; cr = (ss - I.sl * I.ur) * r; break; }
+    case PAS_HLLC_L: cl = I.ul + I.sl * (I.a * fast_rcp(I.b) - 1.0); break;
+    case PAS_HLLC_R: cr = I.ur + I.sr * (I.a * fast_rcp(I.b) - 1.0); break;
+    case PAS_HLLD_L: cl = I.a * I.b * fast_rcp(I.c); break;
+    case PAS_HLLD_R: cr = I.a * I.b * fast_rcp(I.c); break;
+  }
+}
+#endif
 __device__ __forceinline__ double passive_flux(const PasInfo& I, double ql, double qr) {
   switch (I.mode) {
     case PAS_UPL: return ql * I.ul;                                       // prim2f(L): hydro_core.f90:472

@@ -108,3 +108,48 @@ def test_exo_reduced_grid_three_steps(strict, cool):
     uo = interior(o.get_block(0, U))
     err = rel_err_per_var(ug, uo)
     assert err.max() <= 1e-12, err
+
+
+def _run_exo_plugin_vs_oracle(nx, ny, nz, nsteps, strict):
+    """The product-side EXO plugin (guacho_b200/exo.py: its own initial conditions and functor placement) against the oracle's
+    restatement of EXO/user_mod.f90 + EXO/exoplanet.f90, COOL_H included (EXO exactly as shipped)."""
+    from guacho_b200.solver import Block
+    from guacho_b200.exo import Exo, exo_params as plugin_params
+    p = plugin_params(nx, ny, nz, strict_fp=strict)
+    # ONE oracle block: with eta != 0 the reference depends on the block decomposition (viscous_copy reads stale ghosts, SURVEY Q5),
+    # so the one-GPU run is compared with the one-rank reference
+    o = Oracle(p, threads=1)
+    o.L.orc_init_exo(o.h, *[C.c_double(v) for v in scalings(p)])
+    o.L.orc_exo_initial_conditions(o.h)
+    o.start()
+    ex = Exo(p)
+    with Block(p) as b:
+        ex.attach(b, 0.0)
+        b.set_state(ex.initial_conditions())
+        t, it = 0.0, 1
+        for _ in range(nsteps):
+            dt_o, _ = o.get_timestep(it, 10, t, 1e300)
+            dt_g, _ = b.get_timestep(it, 10, t, 1e300)
+            assert abs(dt_g - dt_o) <= 1e-12 * dt_o, (dt_g, dt_o)
+            o.time = t
+            assert o.tstep(dt_o) == 0
+            b.set_time(t)
+            b.tstep(dt_o)
+            t += dt_o
+            it += 1
+        ug = interior(b.get_state())
+    uo = o.gather(U)
+    return rel_err_per_var(ug, uo)
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_exo_plugin_reduced_grid(strict):
+    err = _run_exo_plugin_vs_oracle(96, 24, 96, 3, strict)
+    assert err.max() <= 1e-12, err
+
+
+def test_exo_as_shipped_400x100x400_one_step():
+    """BASELINE configs[3] at its shipped size (EXO/parameters.f90:137-145: 400 x 100 x 400), one step of the production kernels
+    against the oracle (one block, like the one-GPU run; ~30 s of CPU)."""
+    err = _run_exo_plugin_vs_oracle(400, 100, 400, 1, False)
+    assert err.max() <= 1e-12, err

@@ -1,0 +1,11 @@
+mkdir -p gpurun_out/r2
+timeout 1200 python -m pytest tests/test_exo_gpu.py -m gpu -x -q --durations=5 2>&1 | tail -12
+timeout 600 python bench.py --problem exo --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2/bench_exo_fused.json 2> gpurun_out/r2/bench_exo_fused.err; python - <<'PY'
+import json
+try:
+    d=json.loads([l for l in open('gpurun_out/r2/bench_exo_fused.json') if l.startswith('{')][-1])
+    print(d['value']/1e9, d['ms_per_step'], d['config']['path'], d['roofline']['kernel_ms_per_step'], d['roofline']['whole_step']['frac'], d['e2e']['ms_per_step'])
+except Exception as e: print('ERR', e)
+PY
+tail -3 gpurun_out/r2/bench_exo_fused.err
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
