@@ -84,7 +84,6 @@ struct gx_solver {
   struct DevScalars { unsigned long long dtmin_bits; int err; int pad; }* dscal = nullptr;   // device
   DevScalars* hscal = nullptr;                                // pinned host mirror
   bool have_state = false;
-  bool fills_by_caller = false;   // overlapped step: it launches the periodic x / y fills itself (boundary planes first)
   bool ghosts_stale = false;   // self-periodic ghost layers of u/up not materialised since the last fused step
   bool fused = false;      // fused stage kernels (gx_stage.cu); otherwise the pass-per-routine kernels
   int kz = 0;              // planes one CTA of the fused stage kernel marches through (0: the launcher fills whole waves of SMs; GX_KZ overrides)
@@ -184,34 +183,6 @@ __global__ void k_bc_face(Grid g, int nvar, double* __restrict__ A, int dir, int
       A[q * g.vs + cd] = (q == negvar) ? -v : v;
     }
   }
-}
-
-// Periodic ghost layers of a block that is its own neighbour in x / y, planes k0..k1 (Fortran k), for the arrays the TMA loaders
-// of the fused stage kernels read (they cannot wrap an index).  Same copies as k_bc_face mode 0, laid out for the memory system:
-//   x: one thread per (row, plane, variable, side) moves the nl cells of that row end (a 16-byte pair for nl = 2: both ends of a
-//      row sit on even elements) — rows j = 1..ny; the corner columns come from the y pass, which runs second over i = 1-nl..nx+nl;
-//   y: one thread per cell of a ghost row, x fastest: whole rows, coalesced.
-__global__ void __launch_bounds__(128) k_fill_x_periodic(Grid g, int nvar, double* __restrict__ A, int nl, int k0) {
-  const int j = (int)(blockIdx.x * blockDim.x + threadIdx.x) + 1;
-  if (j > g.ny) return;
-  const int k = (int)blockIdx.y + k0;
-  const int q = (int)blockIdx.z >> 1, side = (int)blockIdx.z & 1;
-  double* row = A + (long long)q * g.vs + g.idx(0, j, k);          // element of Fortran i = 0
-  if (nl == 2) {
-    if (side == 0) *reinterpret_cast<double2*>(row - 1) = *reinterpret_cast<const double2*>(row + g.nx - 1);       // i = -1, 0 <- nx-1, nx
-    else *reinterpret_cast<double2*>(row + g.nx + 1) = *reinterpret_cast<const double2*>(row + 1);                 // i = nx+1, nx+2 <- 1, 2
-  } else {
-    if (side == 0) row[0] = row[g.nx];
-    else row[g.nx + 1] = row[1];
-  }
-}
-__global__ void __launch_bounds__(128) k_fill_y_periodic(Grid g, int nvar, double* __restrict__ A, int nl, int k0) {
-  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) + 1 - nl;
-  if (i > g.nx + nl) return;
-  const int k = (int)blockIdx.y + k0;
-  const int q = (int)blockIdx.z / (2 * nl), r = (int)blockIdx.z - q * 2 * nl, side = r / nl, l = r - side * nl;
-  const int jd = side == 0 ? 1 - nl + l : g.ny + 1 + l, js = side == 0 ? jd + g.ny : jd - g.ny;
-  A[(long long)q * g.vs + g.idx(i, jd, k)] = A[(long long)q * g.vs + g.idx(i, js, k)];
 }
 
 // pack / unpack a box [lo,hi] (Fortran indices, inclusive) of nvar variables to/from a contiguous buffer
@@ -523,20 +494,6 @@ static void launch_bc_face(gx_solver* s, double* A, int nvar, int dir, int side,
   k_bc_face<<<grid, 64, 0, s->stream>>>(g, nvar, A, dir, side, mode, nl, negvar);
 }
 
-// x / y periodic ghost layers of planes k0..k1 with the lean kernels (only self-periodic directions; see k_fill_x_periodic)
-static void fill_xy_periodic(gx_solver* s, double* A, int nvar, int nl, int k0, int k1, cudaStream_t st) {
-  const Grid& g = s->A.g;
-  if (k1 < k0) return;
-  if (s->nb[0] == 1 && s->periodic[0]) {
-    LaunchScope ls(s, gx::KC_BC);
-    k_fill_x_periodic<<<dim3((g.ny + 127) / 128, k1 - k0 + 1, 2 * nvar), 128, 0, st>>>(g, nvar, A, nl, k0);
-  }
-  if (s->nb[1] == 1 && s->periodic[1]) {
-    LaunchScope ls(s, gx::KC_BC);
-    k_fill_y_periodic<<<dim3((g.nx + 2 * nl + 127) / 128, k1 - k0 + 1, 2 * nl * nvar), 128, 0, st>>>(g, nvar, A, nl, k0);
-  }
-}
-
 // kind 0: conserved/primitive array (closed wall flips normal momentum, boundaries.f90:146-199, 361-438)
 // kind 1: electric field (closed wall flips e(1) on x walls, e(2) on y walls, nothing on z walls,
 //         flux_cd_module.f90:143-192)
@@ -546,9 +503,6 @@ static void fill_xy_periodic(gx_solver* s, double* A, int nvar, int nl, int k0, 
 // download entry points use, so that gx_get_state / gx_get_up are NOT collective calls.
 static int apply_boundaries(gx_solver* s, double* A, int nvar, int nl, int kind, bool skip_wrapped = false, cudaStream_t st = nullptr,
                             bool local_only = false) {
-  // ... except the stage loaders in x and y when they read ghost cells as they are (TMA): u / up keep those layers current
-  // (the overlapped step places these fills itself, around its boundary-first launches)
-  if (skip_wrapped && kind == 0 && s->A.ldghost && !s->fills_by_caller) fill_xy_periodic(s, A, nvar, nl, 1, s->A.g.nz, st ? st : s->stream);
   for (int dir = 0; dir < 3; ++dir) {
     if (s->nb[dir] == 1 && s->periodic[dir]) {            // neighbour is the block itself
       if (skip_wrapped && s->A.wrap[dir]) continue;       // the fused kernels wrap their reads instead
@@ -739,12 +693,11 @@ int gx_create(const gx_config* c, gx_solver** out) {
   s->kz = 0;                                        // planes per CTA of the fused stage kernels: chosen by their launcher
   if (const char* e = getenv("GX_KZ")) s->kz = std::max(1, atoi(e));
   // a user boundary functor may write ghost cells, so ghosts must be real arrays then
-  for (int d = 0; d < 3; ++d) s->A.wrap[d] = (s->fused && s->periodic[d] && s->nb[d] == 1 && !c->bc_user && !getenv("GX_NO_WRAP")) ? 1 : 0;
-  // The loaders of the fused headline kernels are ONE TMA tile load per plane (GX_TMA=0: per-thread cp.async).  TMA reads ghost cells
-  // as they are, so where x / y are self-periodic their ghost layers of u / up are kept current by the lean fill kernels
-  // (fill_xy_periodic) instead of being wrapped in the loaders; z still wraps through the box coordinate.
-  s->A.tma = (fuse_a && s->fused && !(getenv("GX_TMA") && !atoi(getenv("GX_TMA")))) ? 1 : 0;
-  s->A.ldghost = (s->A.tma && (s->A.wrap[0] || s->A.wrap[1])) ? 1 : 0;
+  // (eta != 0: viscous_copy reads up's ghost cells — the half-step halo, SURVEY Q5 — so they must be real arrays as well)
+  for (int d = 0; d < 3; ++d) s->A.wrap[d] = (s->fused && s->periodic[d] && s->nb[d] == 1 && !c->bc_user && c->eta == 0.0 && !getenv("GX_NO_WRAP")) ? 1 : 0;
+  // the loaders of the fused headline kernels are ONE TMA tile load per plane (GX_TMA=0: per-thread cp.async everywhere)
+  // GX_TMA = 0: cp.async everywhere; 1 (default): TMA for the second-order stage; 2: both stages
+  s->A.tma = (fuse_a && s->fused) ? (getenv("GX_TMA") ? atoi(getenv("GX_TMA")) : 1) : 0;
   ALLOC(s->U, var_bytes * g.neq);
   ALLOC(s->UP, var_bytes * g.neq);
   if (!s->fused) {                                   // primitives and face fluxes only exist in HBM on the unfused path
@@ -945,17 +898,9 @@ static int tstep_enqueue_fused_overlap(gx_solver* s, double dt_cfl) {
   };
   auto bupdate = [&](double dt, const double* Ub, double* dst, int nl, unsigned long long* dtmin, int want_cfl) -> int {
     for (const StepArgs* a : {&blo, &bhi}) { LaunchScope ls(s, gx::KC_BUPDATE); K->bupdate(*a, dt, Ub, s->E, dst, dtmin, want_cfl, s->stream); }
-    if (s->A.ldghost) {       // the planes that travel carry their own periodic x / y ghost layers (the neighbour's loader reads them)
-      fill_xy_periodic(s, dst, neq, nl, 1, 2, s->stream);
-      fill_xy_periodic(s, dst, neq, nl, nz - 1, nz, s->stream);
-    }
     fork();
-    s->fills_by_caller = true;
-    int r = apply_boundaries(s, dst, neq, nl, 0, true, s->cstream);                     // boundaryII (nl = 2) / boundaryI (nl = 1)
-    s->fills_by_caller = false;
-    if (r) return r;
+    int r = apply_boundaries(s, dst, neq, nl, 0, true, s->cstream); if (r) return r;    // boundaryII (nl = 2) / boundaryI (nl = 1)
     { LaunchScope ls(s, gx::KC_BUPDATE); K->bupdate(bmid, dt, Ub, s->E, dst, dtmin, want_cfl, s->stream); }
-    if (s->A.ldghost) fill_xy_periodic(s, dst, neq, nl, 3, nz - 2, s->stream);
     join();
     return GX_OK;
   };

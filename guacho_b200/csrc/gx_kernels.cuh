@@ -36,9 +36,7 @@ struct StepArgs {
   int wrap[3];             // direction is periodic with the block as its own neighbour: the fused
                            // kernels read the wrapped cell instead of a ghost cell (ghosts are
                            // then only materialised when the host asks for the arrays)
-  int tma;                 // stage the planes of the fused stage kernels with TMA tile loads (one per plane) instead of per-thread cp.async
-  int ldghost;             // the stage loaders read the x / y ghost cells of u / up as they are (TMA cannot wrap an index): those layers are
-                           // kept current by the periodic fill kernels; wrap[] then only steers the E stencil of the flux-CD update and z
+  int tma;                 // TMA tile loads (one per staged plane) instead of per-thread cp.async: 0 off, 1 second-order stage, 2 both stages
   int kbeg, klast;         // planes (Fortran k) the fused stage / B-update launch covers; 1..nz unless the step is split into
                            // boundary-first and interior launches to overlap the halo exchange (multi-GPU)
   gxp::Phys phys;

@@ -155,6 +155,16 @@ def test_physical_boundaries(bc):
     assert rel_err_per_var(ug, uo).max() <= TOL
 
 
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("solver,mhd,cd", [(SOLVER_HLLD, True, True), (SOLVER_HLLC, False, False)])
+def test_viscosity_on_the_fused_path_periodic(solver, mhd, cd, strict):
+    """eta != 0 with the fused stage kernels on a periodic box: viscous_copy (src/hydro_solver.f90:54-63) reads up's ghost cells,
+    which hold the half-step halo — they must be materialised even though the stage loaders could wrap."""
+    p = Params(nxtot=40, nytot=24, nztot=20, zmax=1.0, mhd=mhd, riemann_solver=solver, enable_flux_cd=cd, eta=0.02, strict_fp=strict)
+    ug, uo, _, _ = run_pair(p, "random", nsteps=3)
+    assert rel_err_per_var(ug, uo).max() <= TOL
+
+
 def test_eight_wave_and_viscosity_and_passives():
     p = Params(nxtot=24, nytot=20, nztot=16, zmax=1.0, enable_flux_cd=False, eight_wave=True, eta=0.01, npas=2, strict_fp=True)
     ug, uo, _, _ = run_pair(p, "random", nsteps=3)
