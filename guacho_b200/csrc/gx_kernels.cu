@@ -248,11 +248,14 @@ __global__ void __launch_bounds__(128) k_viscous2(const StepArgs A, double eta, 
 #ifndef GX_BU_Z
 #define GX_BU_Z 2
 #endif
+// One thread = TWO x-adjacent cells (i, i+1), i odd: every centre / y / z neighbour access is one aligned 16-byte load (rows start
+// on a 128-byte line and i = 1 sits on an even element), the x neighbours i-1 and i+2 are two scalar loads: half the load
+// instructions and twice the bytes per request of the one-cell form.
 template <bool CFL>
-__global__ void __launch_bounds__(32 * GX_BU_Y * GX_BU_Z) k_bupdate(const StepArgs A, double dt, const double* Ub, const double* __restrict__ E,
-                                                                    double* dst, unsigned long long* dtmin_bits) {
+__global__ void __launch_bounds__(32 * GX_BU_Y * GX_BU_Z) k_bupdate(const StepArgs A, const double dtdx, const double dtdy, const double dtdz,
+                                                                    const double* Ub, const double* __restrict__ E, double* dst, unsigned long long* dtmin_bits) {
   const Grid& g = A.g;
-  const int i = (int)(blockIdx.x * 32 + threadIdx.x) + 1, j = (int)(blockIdx.y * GX_BU_Y + threadIdx.y) + 1;
+  const int i = 2 * (int)(blockIdx.x * 32 + threadIdx.x) + 1, j = (int)(blockIdx.y * GX_BU_Y + threadIdx.y) + 1;
   const int k = (int)(blockIdx.z * GX_BU_Z + threadIdx.z) + A.kbeg;
 #if defined(GX_FLAVOUR_FAST)
   double inv_dtp = 0.0;                           // max over cells of (|v| + c) / dx: one reciprocal per CTA instead of three divisions per cell
@@ -260,33 +263,61 @@ __global__ void __launch_bounds__(32 * GX_BU_Y * GX_BU_Z) k_bupdate(const StepAr
   double dtp = 1.e30;
 #endif
   if (i <= g.nx && j <= g.ny && k <= A.klast) {
+    const bool two = i + 1 <= g.nx;               // (odd nx: the last thread of a row owns one cell; its second lane of work is discarded)
     const long long c = g.idx(i, j, k), sy = g.px, sz = (long long)g.px * g.py, vs = g.vs;
-    const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
     // neighbours of the E stencil; a self-periodic direction wraps instead of reading a ghost cell
-    const long long xm = (A.wrap[0] && i == 1) ? c + (g.nx - 1) : c - 1, xp = (A.wrap[0] && i == g.nx) ? c - (g.nx - 1) : c + 1;
+    const long long xm = (A.wrap[0] && i == 1) ? c + (g.nx - 1) : c - 1;                         // left of cell i
+    const long long xp = (A.wrap[0] && i + 1 >= g.nx) ? c + 1 - (g.nx - 1) : c + 2;              // right of cell i+1
     const long long ym = (A.wrap[1] && j == 1) ? c + (g.ny - 1) * sy : c - sy, yp = (A.wrap[1] && j == g.ny) ? c - (g.ny - 1) * sy : c + sy;
     const long long zm = (A.wrap[2] && k == 1) ? c + (g.nz - 1) * sz : c - sz, zp = (A.wrap[2] && k == g.nz) ? c - (g.nz - 1) * sz : c + sz;
-    const double bx = Ub[5 * vs + c] - 0.5 * dtdy * (E[2 * vs + yp] - E[2 * vs + ym]) + 0.5 * dtdz * (E[1 * vs + zp] - E[1 * vs + zm]);
-    const double by = Ub[6 * vs + c] + 0.5 * dtdx * (E[2 * vs + xp] - E[2 * vs + xm]) - 0.5 * dtdz * (E[0 * vs + zp] - E[0 * vs + zm]);
-    const double bz = Ub[7 * vs + c] - 0.5 * dtdx * (E[1 * vs + xp] - E[1 * vs + xm]) + 0.5 * dtdy * (E[0 * vs + yp] - E[0 * vs + ym]);
-    dst[5 * vs + c] = bx; dst[6 * vs + c] = by; dst[7 * vs + c] = bz;
+    auto ld2 = [](const double* p) { return *reinterpret_cast<const double2*>(p); };
+    const double2 b5 = ld2(Ub + 5 * vs + c), b6 = ld2(Ub + 6 * vs + c), b7 = ld2(Ub + 7 * vs + c);
+    const double2 e2yp = ld2(E + 2 * vs + yp), e2ym = ld2(E + 2 * vs + ym), e1zp = ld2(E + 1 * vs + zp), e1zm = ld2(E + 1 * vs + zm);
+    const double2 e0zp = ld2(E + 0 * vs + zp), e0zm = ld2(E + 0 * vs + zm), e0yp = ld2(E + 0 * vs + yp), e0ym = ld2(E + 0 * vs + ym);
+    double2 e2c = ld2(E + 2 * vs + c), e1c = ld2(E + 1 * vs + c);
+    const double e2l = E[2 * vs + xm], e2r = E[2 * vs + xp], e1l = E[1 * vs + xm], e1r = E[1 * vs + xp];
+    if (!two && A.wrap[0]) {                      // odd nx, last cell of a wrapped row: its right neighbour is cell 1, not the ghost cell
+      e2c.y = E[2 * vs + c - (g.nx - 1)];
+      e1c.y = E[1 * vs + c - (g.nx - 1)];
+    }
+    // flux_cd_update, src/flux_cd_module.f90:311-321 (cell i: .x, cell i+1: .y); x differences: (E(i+1) - E(i-1)) and (E(i+2) - E(i))
+    double2 bx, by, bz;
+    bx.x = b5.x - 0.5 * dtdy * (e2yp.x - e2ym.x) + 0.5 * dtdz * (e1zp.x - e1zm.x);
+    bx.y = b5.y - 0.5 * dtdy * (e2yp.y - e2ym.y) + 0.5 * dtdz * (e1zp.y - e1zm.y);
+    by.x = b6.x + 0.5 * dtdx * (e2c.y - e2l) - 0.5 * dtdz * (e0zp.x - e0zm.x);
+    by.y = b6.y + 0.5 * dtdx * (e2r - e2c.x) - 0.5 * dtdz * (e0zp.y - e0zm.y);
+    bz.x = b7.x - 0.5 * dtdx * (e1c.y - e1l) + 0.5 * dtdy * (e0yp.x - e0ym.x);
+    bz.y = b7.y - 0.5 * dtdx * (e1r - e1c.x) + 0.5 * dtdy * (e0yp.y - e0ym.y);
+    if (two) {
+      *reinterpret_cast<double2*>(dst + 5 * vs + c) = bx; *reinterpret_cast<double2*>(dst + 6 * vs + c) = by; *reinterpret_cast<double2*>(dst + 7 * vs + c) = bz;
+    } else {
+      dst[5 * vs + c] = bx.x; dst[6 * vs + c] = by.x; dst[7 * vs + c] = bz.x;
+    }
     if (CFL) {
-      double u[8], w[8], T;
+      double2 d5[5];
 #pragma unroll
-      for (int q = 0; q < 5; ++q) u[q] = dst[q * vs + c];
-      u[5] = bx; u[6] = by; u[7] = bz;
-      gxp::u2prim<true>(A.phys, u, w, g.npas > 0 ? dst[8 * vs + c] : 0.0, T);    // EOS_H_RATE reads the first passive
-      double cx, cy, cz;
-      gxp::cfast3(A.phys, w[4], w[0], w[5], w[6], w[7], cx, cy, cz);
+      for (int q = 0; q < 5; ++q) d5[q] = ld2(dst + q * vs + c);
+      const double2 pas = g.npas > 0 ? ld2(dst + 8 * vs + c) : make_double2(0.0, 0.0);          // EOS_H_RATE reads the first passive
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        if (m == 1 && !two) break;
+        double u[8], w[8], T;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) u[q] = m ? d5[q].y : d5[q].x;
+        u[5] = m ? bx.y : bx.x; u[6] = m ? by.y : by.x; u[7] = m ? bz.y : bz.x;
+        gxp::u2prim<true>(A.phys, u, w, m ? pas.y : pas.x, T);
+        double cx, cy, cz;
+        gxp::cfast3(A.phys, w[4], w[0], w[5], w[6], w[7], cx, cy, cz);
 #if defined(GX_FLAVOUR_FAST)
-      inv_dtp = gxp::gx_max(inv_dtp, (fabs(w[1]) + cx) * A.idx3[0]);
-      inv_dtp = gxp::gx_max(inv_dtp, (fabs(w[2]) + cy) * A.idx3[1]);
-      inv_dtp = gxp::gx_max(inv_dtp, (fabs(w[3]) + cz) * A.idx3[2]);
+        inv_dtp = gxp::gx_max(inv_dtp, (fabs(w[1]) + cx) * A.idx3[0]);
+        inv_dtp = gxp::gx_max(inv_dtp, (fabs(w[2]) + cy) * A.idx3[1]);
+        inv_dtp = gxp::gx_max(inv_dtp, (fabs(w[3]) + cz) * A.idx3[2]);
 #else
-      dtp = fmin(dtp, g.dx / (fabs(w[1]) + cx));
-      dtp = fmin(dtp, g.dy / (fabs(w[2]) + cy));
-      dtp = fmin(dtp, g.dz / (fabs(w[3]) + cz));
+        dtp = fmin(dtp, g.dx / (fabs(w[1]) + cx));
+        dtp = fmin(dtp, g.dy / (fabs(w[2]) + cy));
+        dtp = fmin(dtp, g.dz / (fabs(w[3]) + cz));
 #endif
+      }
     }
   }
   if (CFL) {
@@ -412,9 +443,10 @@ static int l_stage(const StepArgs& A, int order, double dt, const double* S, con
 static void l_bupdate(const StepArgs& A, double dt, const double* Ub, const double* E, double* dst, unsigned long long* dtmin_bits, int want_cfl, cudaStream_t s) {
   const Grid& g = A.g;
   const dim3 block(32, GX_BU_Y, GX_BU_Z);
-  const dim3 grid((g.nx + 31) / 32, (g.ny + GX_BU_Y - 1) / GX_BU_Y, (A.klast - A.kbeg + 1 + GX_BU_Z - 1) / GX_BU_Z);
-  if (want_cfl) k_bupdate<true><<<grid, block, 0, s>>>(A, dt, Ub, E, dst, dtmin_bits);
-  else k_bupdate<false><<<grid, block, 0, s>>>(A, dt, Ub, E, dst, dtmin_bits);
+  const dim3 grid((g.nx + 63) / 64, (g.ny + GX_BU_Y - 1) / GX_BU_Y, (A.klast - A.kbeg + 1 + GX_BU_Z - 1) / GX_BU_Z);
+  const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
+  if (want_cfl) k_bupdate<true><<<grid, block, 0, s>>>(A, dtdx, dtdy, dtdz, Ub, E, dst, dtmin_bits);
+  else k_bupdate<false><<<grid, block, 0, s>>>(A, dtdx, dtdy, dtdz, Ub, E, dst, dtmin_bits);
 }
 
 static const KernelTable table = {l_calcprim, l_fluxes, l_efield, l_update, l_viscous, l_viscous2, l_stage, l_bupdate, l_riemann_points};
