@@ -664,7 +664,7 @@ int gx_create(const gx_config* c, gx_solver** out) {
   s->A.solver = c->riemann_solver; s->A.limiter = c->slope_limiter;
   s->A.flux_cd = c->enable_flux_cd; s->A.eight_wave = c->eight_wave; s->A.user_src = c->user_source_terms;
   s->A.grav.n = 0;
-  s->A.kbeg = 1; s->A.klast = nz;
+  s->A.kbeg = 1; s->A.klast = nz; s->A.kbeg2 = 1; s->A.klast2 = 0;
   s->K = c->strict_fp ? gx::kernels_strict() : gx::kernels_fast();
 
   s->nb[0] = c->nbx; s->nb[1] = c->nby; s->nb[2] = c->nbz;
@@ -878,17 +878,18 @@ static int tstep_enqueue_fused_overlap(gx_solver* s, double dt_cfl) {
   const int neq = s->A.g.neq, nz = s->A.g.nz;
   const double dtm = dt_cfl / 2.;
   const int kb = 4;                                   // boundary thickness of the stage launches (>= 2: up sends 2 layers)
-  StepArgs lo = s->A, hi = s->A, mid = s->A;
-  lo.kbeg = 1; lo.klast = kb; hi.kbeg = nz - kb + 1; hi.klast = nz; mid.kbeg = kb + 1; mid.klast = nz - kb;
-  StepArgs blo = s->A, bhi = s->A, bmid = s->A;       // B update: exactly the layers that travel
-  blo.kbeg = 1; blo.klast = 2; bhi.kbeg = nz - 1; bhi.klast = nz; bmid.kbeg = 3; bmid.klast = nz - 2;
+  // the two boundary slabs of a kernel go out as ONE launch (second plane range of StepArgs): one tail instead of two
+  StepArgs bnd = s->A, mid = s->A;
+  bnd.kbeg = 1; bnd.klast = kb; bnd.kbeg2 = nz - kb + 1; bnd.klast2 = nz; mid.kbeg = kb + 1; mid.klast = nz - kb;
+  StepArgs bbnd = s->A, bmid = s->A;                  // B update: exactly the layers that travel
+  bbnd.kbeg = 1; bbnd.klast = 2; bbnd.kbeg2 = nz - 1; bbnd.klast2 = nz; bmid.kbeg = 3; bmid.klast = nz - 2;
   int rc;
   auto fork = [&]() { cudaEventRecord(s->ev_bnd, s->stream); cudaStreamWaitEvent(s->cstream, s->ev_bnd, 0); };
   auto join = [&]() { cudaEventRecord(s->ev_comm, s->cstream); cudaStreamWaitEvent(s->stream, s->ev_comm, 0); };
   auto stage = [&](int cls, int order, double dt, const double* S, const double* Ub, double* dst) -> int {
-    for (const StepArgs* a : {&lo, &hi}) {
+    {
       LaunchScope ls(s, cls);
-      int r = K->stage(*a, order, dt, S, Ub, dst, s->E, s->kz, nullptr, 0, &s->dscal->err, s->stream); if (r) return r;
+      int r = K->stage(bnd, order, dt, S, Ub, dst, s->E, s->kz, nullptr, 0, &s->dscal->err, s->stream); if (r) return r;
     }
     fork();
     int r = apply_boundaries(s, s->E, 3, 1, 1, true, s->cstream); if (r) return r;      // boundaryI_ef
@@ -897,7 +898,7 @@ static int tstep_enqueue_fused_overlap(gx_solver* s, double dt_cfl) {
     return GX_OK;
   };
   auto bupdate = [&](double dt, const double* Ub, double* dst, int nl, unsigned long long* dtmin, int want_cfl) -> int {
-    for (const StepArgs* a : {&blo, &bhi}) { LaunchScope ls(s, gx::KC_BUPDATE); K->bupdate(*a, dt, Ub, s->E, dst, dtmin, want_cfl, s->stream); }
+    { LaunchScope ls(s, gx::KC_BUPDATE); K->bupdate(bbnd, dt, Ub, s->E, dst, dtmin, want_cfl, s->stream); }
     fork();
     int r = apply_boundaries(s, dst, neq, nl, 0, true, s->cstream); if (r) return r;    // boundaryII (nl = 2) / boundaryI (nl = 1)
     { LaunchScope ls(s, gx::KC_BUPDATE); K->bupdate(bmid, dt, Ub, s->E, dst, dtmin, want_cfl, s->stream); }

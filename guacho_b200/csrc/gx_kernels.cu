@@ -256,13 +256,16 @@ __global__ void __launch_bounds__(32 * GX_BU_Y * GX_BU_Z) k_bupdate(const StepAr
                                                                     const double* Ub, const double* __restrict__ E, double* dst, unsigned long long* dtmin_bits) {
   const Grid& g = A.g;
   const int i = 2 * (int)(blockIdx.x * 32 + threadIdx.x) + 1, j = (int)(blockIdx.y * GX_BU_Y + threadIdx.y) + 1;
-  const int k = (int)(blockIdx.z * GX_BU_Z + threadIdx.z) + A.kbeg;
+  const int nz1 = (A.klast - A.kbeg + GX_BU_Z) / GX_BU_Z;              // z blocks of the first plane range; then the second (see StepArgs)
+  const bool second = (int)blockIdx.z >= nz1;
+  const int k = second ? (int)((blockIdx.z - nz1) * GX_BU_Z + threadIdx.z) + A.kbeg2 : (int)(blockIdx.z * GX_BU_Z + threadIdx.z) + A.kbeg;
+  const int klast = second ? A.klast2 : A.klast;
 #if defined(GX_FLAVOUR_FAST)
   double inv_dtp = 0.0;                           // max over cells of (|v| + c) / dx: one reciprocal per CTA instead of three divisions per cell
 #else
   double dtp = 1.e30;
 #endif
-  if (i <= g.nx && j <= g.ny && k <= A.klast) {
+  if (i <= g.nx && j <= g.ny && k <= klast) {
     const bool two = i + 1 <= g.nx;               // (odd nx: the last thread of a row owns one cell; its second lane of work is discarded)
     const long long c = g.idx(i, j, k), sy = g.px, sz = (long long)g.px * g.py, vs = g.vs;
     // neighbours of the E stencil; a self-periodic direction wraps instead of reading a ghost cell
@@ -443,7 +446,8 @@ static int l_stage(const StepArgs& A, int order, double dt, const double* S, con
 static void l_bupdate(const StepArgs& A, double dt, const double* Ub, const double* E, double* dst, unsigned long long* dtmin_bits, int want_cfl, cudaStream_t s) {
   const Grid& g = A.g;
   const dim3 block(32, GX_BU_Y, GX_BU_Z);
-  const dim3 grid((g.nx + 63) / 64, (g.ny + GX_BU_Y - 1) / GX_BU_Y, (A.klast - A.kbeg + 1 + GX_BU_Z - 1) / GX_BU_Z);
+  const int n2 = A.klast2 >= A.kbeg2 ? A.klast2 - A.kbeg2 + 1 : 0;
+  const dim3 grid((g.nx + 63) / 64, (g.ny + GX_BU_Y - 1) / GX_BU_Y, (A.klast - A.kbeg + 1 + GX_BU_Z - 1) / GX_BU_Z + (n2 + GX_BU_Z - 1) / GX_BU_Z);
   const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
   if (want_cfl) k_bupdate<true><<<grid, block, 0, s>>>(A, dtdx, dtdy, dtdz, Ub, E, dst, dtmin_bits);
   else k_bupdate<false><<<grid, block, 0, s>>>(A, dtdx, dtdy, dtdz, Ub, E, dst, dtmin_bits);

@@ -39,6 +39,8 @@ struct StepArgs {
   int tma;                 // TMA tile loads (one per staged plane) instead of per-thread cp.async: 0 off, 1 second-order stage, 2 both stages
   int kbeg, klast;         // planes (Fortran k) the fused stage / B-update launch covers; 1..nz unless the step is split into
                            // boundary-first and interior launches to overlap the halo exchange (multi-GPU)
+  int kbeg2, klast2;       // second plane range of the same launch (the two boundary slabs of a block go out as ONE launch);
+                           // empty when klast2 < kbeg2
   gxp::Phys phys;
   double idx3[3];          // 1/dx, 1/dy, 1/dz (production kernels: CFL candidates without divisions)
   int solver, limiter;

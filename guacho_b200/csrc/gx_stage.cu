@@ -217,8 +217,12 @@ k_stage(const StepArgs A, const StageDt sdt, const double* __restrict__ S, const
 
   const Grid& g = A.g;
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-  const int i0 = 1 + (int)blockIdx.x * TX, j0 = 1 + (int)blockIdx.y * TY, k0 = A.kbeg + (int)blockIdx.z * kz;
-  const int kend = min(k0 + kz - 1, A.klast);
+  // z chunk of this CTA: the chunks of the first plane range, then those of the second (boundary slabs of the overlapped step)
+  const int nch1 = (A.klast - A.kbeg + kz) / kz;
+  const bool second = (int)blockIdx.z >= nch1;
+  const int i0 = 1 + (int)blockIdx.x * TX, j0 = 1 + (int)blockIdx.y * TY;
+  const int k0 = second ? A.kbeg2 + ((int)blockIdx.z - nch1) * kz : A.kbeg + (int)blockIdx.z * kz;
+  const int kend = min(k0 + kz - 1, second ? A.klast2 : A.klast);
   const long long vs = g.vs;
   const bool main_warp = wrp < TY;                       // warp-uniform
 
@@ -643,8 +647,9 @@ static int launch_one(const StepArgs& A, double dt, const double* S, const doubl
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM) != cudaSuccess) return GX_ECUDA;
   const StageDt sdt = {dt / g.dx, dt / g.dy, dt / g.dz, dt};
   const int tx = (g.nx + G::TX - 1) / G::TX, ty = (g.ny + G::TY - 1) / G::TY, nplanes = A.klast - A.kbeg + 1;
-  if (kz <= 0) kz = auto_kz((long long)tx * ty, nplanes);            // kz > 0: the caller's choice (GX_KZ)
-  dim3 grid(tx, ty, (nplanes + kz - 1) / kz);
+  const int nplanes2 = A.klast2 >= A.kbeg2 ? A.klast2 - A.kbeg2 + 1 : 0;
+  if (kz <= 0) kz = auto_kz((long long)tx * ty * (nplanes2 ? 2 : 1), nplanes);            // kz > 0: the caller's choice (GX_KZ)
+  dim3 grid(tx, ty, (nplanes + kz - 1) / kz + (nplanes2 + kz - 1) / kz);
   kern<<<grid, G::NT, G::SMEM, st>>>(A, sdt, S, Ub, dst, E, kz, dtmin_bits, want_cfl, errflag, tm ? *tm : no_map);
   return GX_OK;
 }
