@@ -13,6 +13,7 @@ from dataclasses import dataclass, field, asdict
 # ---- named constants, values identical to src/constants.f90:56-98 ----
 SOLVER_HLL, SOLVER_HLLC, SOLVER_HLLE, SOLVER_HLLD = 1, 2, 3, 4
 EOS_ADIABATIC, EOS_SINGLE_SPECIE, EOS_H_RATE, EOS_CHEM = 1, 2, 3, 4
+TC_OFF, TC_ISOTROPIC, TC_ANISOTROPIC = 0, 1, 2
 BC_OUTFLOW, BC_CLOSED, BC_PERIODIC, BC_OTHER = 1, 2, 3, 4
 COOL_NONE, COOL_H = 0, 1
 LIMITER_NO_AVERAGE, LIMITER_NO_LIMIT, LIMITER_MINMOD, LIMITER_VAN_LEER = -1, 0, 1, 2
@@ -39,10 +40,12 @@ class GxConfig(C.Structure):
         ("enable_flux_cd", C.c_int32), ("eight_wave", C.c_int32), ("user_source_terms", C.c_int32),
         ("bc_left", C.c_int32), ("bc_right", C.c_int32), ("bc_bottom", C.c_int32),
         ("bc_top", C.c_int32), ("bc_out", C.c_int32), ("bc_in", C.c_int32),
-        ("bc_user", C.c_int32), ("strict_fp", C.c_int32), ("cooling", C.c_int32), ("pad_", C.c_int32),
+        ("bc_user", C.c_int32), ("strict_fp", C.c_int32), ("cooling", C.c_int32),
+        ("th_cond", C.c_int32), ("tc_saturation", C.c_int32), ("pad_", C.c_int32),
         ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double),
         ("cv", C.c_double), ("gamma", C.c_double), ("Tempsc", C.c_double),
         ("cfl", C.c_double), ("eta", C.c_double), ("tsc", C.c_double),
+        ("rsc", C.c_double), ("rhosc", C.c_double), ("vsc2", C.c_double), ("bsc", C.c_double), ("mu", C.c_double),
     ]
 
 
@@ -80,6 +83,13 @@ class Params:
     eta: float = 0.0
     cooling: int = COOL_NONE
     tsc: float = 1.0
+    th_cond: int = 0                 # TC_OFF | TC_ISOTROPIC | TC_ANISOTROPIC (src/constants.f90:96-98)
+    tc_saturation: bool = False
+    rsc: float = 1.0                 # scalings to cgs (parameters.f90:159-170); thermal conduction only
+    rhosc: float = 1.0
+    vsc2: float = 1.0
+    bsc: float = 1.0
+    mu: float = 1.0
     tmax: float = 0.5
     dtprint: float = 0.1
     strict_fp: bool = False
@@ -175,6 +185,8 @@ class Params:
         c.cv, c.gamma, c.Tempsc = self.cv, self.gamma, self.Tempsc
         c.cfl, c.eta = self.cfl, self.eta
         c.cooling, c.tsc = self.cooling, self.tsc
+        c.th_cond, c.tc_saturation = self.th_cond, int(self.tc_saturation)
+        c.rsc, c.rhosc, c.vsc2, c.bsc, c.mu = self.rsc, self.rhosc, self.vsc2, self.bsc, self.mu
         return c
 
     def replace(self, **kw) -> "Params":

@@ -61,7 +61,7 @@ static int nccl_load() {
 #define NCCL_TRY(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) return fail(GX_ECOMM, "%s failed: %s", #x, g_nccl.GetErrorString(r_)); } while (0)
 
 // layout of the boundary struct (include/guacho_gx.h): no implicit padding, the same image in C, ctypes and bind(C)
-static_assert(offsetof(gx_config, pad_) == 33 * 4 && offsetof(gx_config, dx) == 34 * 4 && sizeof(gx_config) == 34 * 4 + 9 * 8,
+static_assert(offsetof(gx_config, pad_) == 35 * 4 && offsetof(gx_config, dx) == 36 * 4 && sizeof(gx_config) == 36 * 4 + 14 * 8,
               "gx_config layout changed: update include/guacho_gx.h, guacho_b200/config.py and guacho_b200/fortran/guacho_gpu.f90 together");
 
 // ---------------------------------------------------------------------------

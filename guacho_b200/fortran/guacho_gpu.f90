@@ -26,8 +26,8 @@ module guacho_gpu
     integer(c_int32_t) :: riemann_solver, slope_limiter, eq_of_state
     integer(c_int32_t) :: enable_flux_cd, eight_wave, user_source_terms
     integer(c_int32_t) :: bc_left, bc_right, bc_bottom, bc_top, bc_out, bc_in
-    integer(c_int32_t) :: bc_user, strict_fp, cooling, pad_
-    real(c_double)     :: dx, dy, dz, cv, gamma, Tempsc, cfl, eta, tsc
+    integer(c_int32_t) :: bc_user, strict_fp, cooling, th_cond, tc_saturation, pad_
+    real(c_double)     :: dx, dy, dz, cv, gamma, Tempsc, cfl, eta, tsc, rsc, rhosc, vsc2, bsc, mu
   end type gx_config
 
   !> image of struct gx_wind_sphere (impose_user_bc functor, EXO/exoplanet.f90:125-266)
@@ -197,9 +197,11 @@ contains
     c%bc_user = merge(1, 0, bc_user)
     c%strict_fp = 0
     c%cooling = merge(cooling, 0, cooling == COOL_H)   ! the other cooling modules stay in the host
+    c%th_cond = th_cond; c%tc_saturation = merge(1, 0, tc_saturation)
     c%pad_ = 0
     c%dx = dx; c%dy = dy; c%dz = dz
     c%cv = cv; c%gamma = gamma; c%Tempsc = Tempsc; c%cfl = cfl; c%eta = eta; c%tsc = tsc
+    c%rsc = rsc; c%rhosc = rhosc; c%vsc2 = vsc2; c%bsc = bsc; c%mu = mu
     call gx_check(gx_create(c, gx_handle), 'gx_create')
   end subroutine gx_initmain
 

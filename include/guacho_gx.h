@@ -43,6 +43,7 @@ enum { GX_LIMITER_NO_AVERAGE = -1, GX_LIMITER_NO_LIMIT = 0, GX_LIMITER_MINMOD = 
        GX_LIMITER_VAN_LEER = 2, GX_LIMITER_VAN_ALBADA = 3, GX_LIMITER_UMIST = 4,
        GX_LIMITER_WOODWARD = 5, GX_LIMITER_SUPERBEE = 6 };
 
+enum { GX_TC_OFF = 0, GX_TC_ISOTROPIC = 1, GX_TC_ANISOTROPIC = 2 };
 enum { GX_COOL_NONE = 0, GX_COOL_H = 1, GX_COOL_BBC = 2, GX_COOL_DMC = 3, GX_COOL_CHI = 4, GX_COOL_CHEM = 5 };
 
 /* ---- error codes ---- */
@@ -51,9 +52,9 @@ enum { GX_OK = 0, GX_EINVAL = -1, GX_ENODEVICE = -2, GX_ECUDA = -3, GX_ENOMEM = 
 
 /* Every Fortran `parameter` the step reads (OT/parameters.f90:48-227) plus the
  * block decomposition that replaces MPI_NBX/NBY/NBZ and mpi_cart_coords
- * (src/init.f90:103-110).  Plain int32/double, no implicit padding: 34 int32 first
- * (33 parameters + one explicit pad word, so the doubles start on an 8-byte offset in
- * every binding, packed or not), then 9 doubles; gx_api.cu static_asserts the offsets. */
+ * (src/init.f90:103-110).  Plain int32/double, no implicit padding: 36 int32 first
+ * (35 parameters + one explicit pad word, so the doubles start on an 8-byte offset in
+ * every binding, packed or not), then 14 doubles; gx_api.cu static_asserts the offsets. */
 typedef struct gx_config {
   int32_t struct_bytes;      /* = sizeof(gx_config); ABI check                         */
   int32_t device;            /* CUDA device ordinal; -1 = keep the current device     */
@@ -74,12 +75,17 @@ typedef struct gx_config {
   int32_t cooling;           /* GX_COOL_*: NONE, or H = the parametrised hydrogen cooling operator
                                 (src/cooling_h.f90:41-67, applied after viscous_copy, hydro_solver.f90:202-204);
                                 it needs EOS_H_RATE-style passives (npas >= 1: neutral H density)   */
+  int32_t th_cond;           /* GX_TC_*: thermal conduction operator at the end of tstep (src/thermal_cond.f90:690-768,
+                                called from hydro_solver.f90:227); OFF, ISOTROPIC (Spitzer), ANISOTROPIC (needs B)        */
+  int32_t tc_saturation;     /* parameters.f90: tc_saturation (saturated heat flux)                          */
   int32_t pad_;              /* explicit padding word (keeps the int32 count even); set to 0                  */
   double dx, dy, dz;         /* globals dx dy dz (src/init.f90:120-122)               */
   double cv, gamma;          /* parameters.f90: cv, gamma=(cv+1)/cv                   */
   double Tempsc;             /* temperature scaling used by u2prim                    */
   double cfl, eta;
-  double tsc;                /* time scaling to seconds (parameters.f90: tsc); used by GX_COOL_H only  */
+  double tsc;                /* time scaling to seconds (parameters.f90: tsc); used by GX_COOL_H and thermal conduction  */
+  double rsc, rhosc, vsc2;   /* length, density and velocity^2 scalings to cgs (parameters.f90:163-167); thermal conduction only  */
+  double bsc, mu;            /* magnetic field scaling, mean atomic mass (parameters.f90:159,170); thermal conduction only        */
 } gx_config;
 
 typedef struct gx_solver gx_solver;   /* opaque; one per block (= per GPU / MPI rank) */

@@ -35,8 +35,8 @@ def test_binding_loads_and_reports_build():
 
 def test_config_struct_matches_header_size():
     # all int32 first (34 of them), then 9 doubles
-    assert C.sizeof(GxConfig) == 34 * 4 + 9 * 8
-    assert GxConfig.pad_.offset == 33 * 4 and GxConfig.dx.offset == 34 * 4 and GxConfig.tsc.offset == 34 * 4 + 8 * 8   # no implicit padding
+    assert C.sizeof(GxConfig) == 36 * 4 + 14 * 8
+    assert GxConfig.pad_.offset == 35 * 4 and GxConfig.dx.offset == 36 * 4 and GxConfig.tsc.offset == 36 * 4 + 8 * 8 and GxConfig.mu.offset == 36 * 4 + 13 * 8   # no implicit padding
     c = Params().to_c()
     assert c.struct_bytes == C.sizeof(GxConfig)
 
