@@ -18,6 +18,7 @@
 
 #include "../../include/guacho_gx.h"
 #include "gx_kernels.cuh"
+#include "gx_thermal.cuh"
 
 using gx::Grid;
 using gx::StepArgs;
@@ -77,11 +78,13 @@ struct gx_solver {
   cudaEvent_t ev_bnd = nullptr, ev_comm = nullptr;
   bool overlap = false;                                       // z slabs + peer push: boundary-first launches, exchange on cstream
   double *U = nullptr, *UP = nullptr, *W = nullptr, *F = nullptr, *E = nullptr, *Temp = nullptr, *T = nullptr;
+  double* PT = nullptr;                                       // thermal conduction: pressure and temperature (2 variables)
+  double tc_dt_cond = 0.0; int tc_nsteps = 0;                 // what the reference logs per call (thermal_cond.f90:725)
   double* stage = nullptr; size_t stage_doubles = 0;         // AoS staging for layout conversion
   double* halo_send[6] = {0, 0, 0, 0, 0, 0};                  // packed faces (multi-GPU)
   double* halo_recv[6] = {0, 0, 0, 0, 0, 0};
   size_t halo_doubles[3] = {0, 0, 0};
-  struct DevScalars { unsigned long long dtmin_bits; int err; int pad; }* dscal = nullptr;   // device
+  struct DevScalars { unsigned long long dtmin_bits; int err; int pad; unsigned long long tc_bits; }* dscal = nullptr;   // device
   DevScalars* hscal = nullptr;                                // pinned host mirror
   bool have_state = false;
   bool ghosts_stale = false;   // self-periodic ghost layers of u/up not materialised since the last fused step
@@ -425,7 +428,12 @@ static bool load_stream_memops() {
   return true;
 }
 static double* peer_array(const gx_solver* s, int side, const double* A) {
-  return A == s->U ? s->peer[side].U : A == s->UP ? s->peer[side].UP : A == s->E ? s->peer[side].E : nullptr;
+  // `A` may point at one variable inside an array (thermal_bounds exchanges u(5) alone)
+  const long long nu = s->A.g.vs * s->A.g.neq, ne = s->A.g.vs * 3;
+  if (s->peer[side].U && A >= s->U && A < s->U + nu) return s->peer[side].U + (A - s->U);
+  if (s->peer[side].UP && A >= s->UP && A < s->UP + nu) return s->peer[side].UP + (A - s->UP);
+  if (s->peer[side].E && s->E && A >= s->E && A < s->E + ne) return s->peer[side].E + (A - s->E);
+  return nullptr;
 }
 static int exchange_z_p2p(gx_solver* s, double* A, int nvar, int nl, cudaStream_t st) {
   const Grid& g = s->A.g;
@@ -636,6 +644,10 @@ int gx_create(const gx_config* c, gx_solver** out) {
   if (c->slope_limiter < -1 || c->slope_limiter > 6) return fail(GX_EINVAL, "unknown slope limiter");
   if (c->cooling != GX_COOL_NONE && c->cooling != GX_COOL_H) return fail(GX_EUNSUPPORTED, "cooling %d stays in the host (only COOL_NONE / COOL_H are device operators)", c->cooling);
   if (c->cooling == GX_COOL_H && (c->npas < 1 || !(c->tsc > 0))) return fail(GX_EINVAL, "COOL_H needs npas >= 1 (neutral H density in u(neqdyn+1)) and tsc > 0");
+  if (c->th_cond < GX_TC_OFF || c->th_cond > GX_TC_ANISOTROPIC) return fail(GX_EINVAL, "unknown th_cond %d", c->th_cond);
+  if (c->th_cond == GX_TC_ANISOTROPIC && !c->mhd) return fail(GX_EINVAL, "anisotropic thermal conduction needs the B field (mhd = 1)");
+  if (c->th_cond != GX_TC_OFF && !(c->tsc > 0 && c->rsc > 0 && c->rhosc > 0 && c->vsc2 > 0 && c->mu > 0 && (c->th_cond == GX_TC_ISOTROPIC || c->bsc > 0)))
+    return fail(GX_EINVAL, "thermal conduction needs the cgs scalings tsc, rsc, rhosc, vsc2, mu (and bsc when anisotropic) > 0");
   if (c->eq_of_state == GX_EOS_CHEM) return fail(GX_EUNSUPPORTED, "EOS_CHEM needs the chemistry network (out of scope)");
   const int bcs[6] = {c->bc_left, c->bc_right, c->bc_bottom, c->bc_top, c->bc_out, c->bc_in};
   for (int b : bcs) if (b < GX_BC_OUTFLOW || b > GX_BC_OTHER) return fail(GX_EINVAL, "unknown boundary condition %d", b);
@@ -693,8 +705,9 @@ int gx_create(const gx_config* c, gx_solver** out) {
   s->kz = 0;                                        // planes per CTA of the fused stage kernels: chosen by their launcher
   if (const char* e = getenv("GX_KZ")) s->kz = std::max(1, atoi(e));
   // a user boundary functor may write ghost cells, so ghosts must be real arrays then
-  // (eta != 0: viscous_copy reads up's ghost cells — the half-step halo, SURVEY Q5 — so they must be real arrays as well)
-  for (int d = 0; d < 3; ++d) s->A.wrap[d] = (s->fused && s->periodic[d] && s->nb[d] == 1 && !c->bc_user && c->eta == 0.0 && !getenv("GX_NO_WRAP")) ? 1 : 0;
+  // (eta != 0: viscous_copy reads up's ghost cells — the half-step halo, SURVEY Q5 — so they must be real arrays as well;
+  //  thermal conduction reads the ghost layer of u)
+  for (int d = 0; d < 3; ++d) s->A.wrap[d] = (s->fused && s->periodic[d] && s->nb[d] == 1 && !c->bc_user && c->eta == 0.0 && c->th_cond == GX_TC_OFF && !getenv("GX_NO_WRAP")) ? 1 : 0;
   // the loaders of the fused headline kernels are ONE TMA tile load per plane (GX_TMA=0: per-thread cp.async everywhere)
   // GX_TMA = 0: cp.async everywhere; 1 (default): TMA for the second-order stage; 2: both stages
   s->A.tma = (fuse_a && s->fused) ? (getenv("GX_TMA") ? atoi(getenv("GX_TMA")) : 1) : 0;
@@ -707,6 +720,7 @@ int gx_create(const gx_config* c, gx_solver** out) {
     ALLOC(s->T, var_bytes * g.neq);                  // full-step state before viscous_copy (up keeps its half-step ghosts)
   }
   if (c->enable_flux_cd) ALLOC(s->E, var_bytes * 3);
+  if (c->th_cond != GX_TC_OFF) ALLOC(s->PT, var_bytes * 2);
   ALLOC(s->dscal, sizeof(gx_solver::DevScalars));
   if (cudaMallocHost((void**)&s->hscal, sizeof(gx_solver::DevScalars)) != cudaSuccess) { s->hscal = nullptr; gx_destroy(s); cudaGetLastError(); return fail(GX_ENOMEM, "cudaMallocHost failed (pinned scalars)"); }
   // staging: up to 64 MiB or 4 planes, whichever is larger
@@ -747,7 +761,7 @@ int gx_destroy(gx_solver* s) {
   }
   if (s->flags) cudaFree(s->flags);
   if (s->comm && g_nccl.ok) g_nccl.CommDestroy(s->comm);
-  double* ptrs[] = {s->U, s->UP, s->W, s->F, s->E, s->Temp, s->T, s->stage};
+  double* ptrs[] = {s->U, s->UP, s->W, s->F, s->E, s->Temp, s->T, s->PT, s->stage};
   for (double* p : ptrs) if (p) cudaFree(p);
   for (int q = 0; q < 6; ++q) { if (s->halo_send[q]) cudaFree(s->halo_send[q]); if (s->halo_recv[q]) cudaFree(s->halo_recv[q]); }
   if (s->dscal) cudaFree(s->dscal);
@@ -764,7 +778,7 @@ int gx_destroy(gx_solver* s) {
 }
 
 static int reset_scalars(gx_solver* s) {          // CFL minimum := +inf, solver error flag := 0 (new state)
-  gx_solver::DevScalars init; init.dtmin_bits = 0x7FF0000000000000ull; init.err = 0; init.pad = 0;
+  gx_solver::DevScalars init; init.dtmin_bits = 0x7FF0000000000000ull; init.err = 0; init.pad = 0; init.tc_bits = 0x7FF0000000000000ull;
   *s->hscal = init;
   CUDA_TRY(cudaMemcpyAsync(s->dscal, s->hscal, sizeof init, cudaMemcpyHostToDevice, s->stream));
   return GX_OK;
@@ -779,6 +793,66 @@ static int ensure_array(gx_solver* s, double** p, size_t nvar) {
   cudaError_t e = cudaMalloc((void**)p, bytes);
   if (e != cudaSuccess) return fail(GX_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
   CUDA_TRY(cudaMemsetAsync(*p, 0, bytes, s->stream));
+  return GX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// thermal_conduction (src/thermal_cond.f90:690-768), called at the end of tstep on u with its ghost layer filled
+// (hydro_solver.f90:216-227).  One host round trip per call: the conduction time scale decides the number of substeps,
+// exactly where the reference does its mpi_allreduce (:104).
+static int thermal_bounds(gx_solver* s) {
+  // :496-616 (MPI branch): one layer of u(5) between blocks, then zero-gradient copies on every face of the DOMAIN whatever
+  // its boundary type — so a periodic direction owned by one block needs no wrap copy at all (it would be overwritten).
+  double* A = s->U + 4 * s->A.g.vs;
+  for (int dir = 0; dir < 3; ++dir) {
+    if (s->nb[dir] == 1) continue;
+    int rc = exchange_dir(s, A, 1, 1, dir); if (rc) return rc;
+  }
+  for (int dir = 0; dir < 3; ++dir)
+    for (int side = 0; side < 2; ++side)
+      if (s->co[dir] == (side == 0 ? 0 : s->nb[dir] - 1)) launch_bc_face(s, A, 1, dir, side, 1, 1, -1);
+  return GX_OK;
+}
+static int thermal_conduction(gx_solver* s, double dt_cfl) {
+  const Grid& g = s->A.g;
+  const gx_config& c = s->cfg;
+  gxtc::TcPar t;
+  t.mode = c.th_cond; t.sat = c.tc_saturation; t.mhd = c.mhd;
+  t.dxr = c.dx * c.rsc; t.dyr = c.dy * c.rsc; t.dzr = c.dz * c.rsc;
+  t.dx = c.dx; t.dy = c.dy; t.dz = c.dz;
+  t.vsc = sqrt(c.vsc2); t.sqrt_vsc2 = sqrt(c.vsc2);
+  t.Psc = c.rhosc * c.vsc2; t.rhosc = c.rhosc; t.bsc2 = c.bsc * c.bsc;
+  const dim3 gp((g.nx + 2 + 127) / 128, g.ny + 2, g.nz + 2), gu((g.nx + 127) / 128, g.ny, g.nz);
+  auto prim = [&](int want_dt) {
+    LaunchScope ls(s, gx::KC_TCOND);
+    gxtc::k_tc_prim<<<gp, 128, 0, s->stream>>>(g, s->A.phys, c.mhd, s->U, s->PT, &s->dscal->tc_bits, want_dt);
+  };
+  // get_dt_cond (:78-110)
+  CUDA_TRY(cudaMemsetAsync(&s->dscal->tc_bits, 0x7f, sizeof(unsigned long long), s->stream));
+  prim(1);
+  if (s->comm && s->nranks > 1) NCCL_TRY(g_nccl.AllReduce(&s->dscal->tc_bits, &s->dscal->tc_bits, 1, ncclUint64, ncclMin, s->comm, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(&s->hscal->tc_bits, &s->dscal->tc_bits, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  double dtp; memcpy(&dtp, &s->hscal->tc_bits, sizeof dtp);
+  double ddx = std::min(c.dx, c.dy);
+  ddx = std::min(ddx, c.dz);
+  // the scaling is a chain of products with positive factors, monotonic under rounding: min first or last is the same number
+  const double dt_cond = 0.25 * 0.5 * ((ddx * c.rsc) * (ddx * c.rsc)) * c.cv * 8.3145e7 * dtp * c.rhosc / c.mu;          // :101
+  const double dt_hydro = dt_cfl * c.tsc;
+  bool SuperStep = true;
+  int Nsteps; double fstep;
+  if (dt_cond < dt_hydro) gxtc::ST_steps(dt_hydro / dt_cond, Nsteps, fstep);
+  else { SuperStep = false; fstep = dt_hydro / dt_cond; Nsteps = 1; }
+  s->tc_dt_cond = dt_cond; s->tc_nsteps = Nsteps;
+  for (int n = 1; n <= Nsteps; ++n) {
+    double dts;
+    if (SuperStep) dts = dt_cond * fstep * gxtc::substep(n, Nsteps, 0.01) / t.Psc / c.rsc;                                 // :732
+    else dts = dt_hydro / (double)Nsteps / t.Psc / c.rsc;
+    { LaunchScope ls(s, gx::KC_TCOND); gxtc::k_tc_update<<<gu, 128, 0, s->stream>>>(g, s->A.phys, t, s->PT, s->U, dts); }
+    int rc = thermal_bounds(s); if (rc) return rc;
+    if (n < Nsteps) prim(0);                         // calcprim (:764); after the last substep the caller's calcprim pass does it
+  }
+  CUDA_TRY(cudaGetLastError());
   return GX_OK;
 }
 
@@ -848,7 +922,7 @@ static int tstep_enqueue_fused(gx_solver* s, double dt_cfl) {
   // eta == 0: viscous_copy is u(interior) = up(interior), so the full step goes straight into u.  eta != 0: it goes into T and
   // viscous_copy (hydro_solver.f90:54-63) reads T inside the block and up — the half-step halo of boundaryII — in the ghost cells
   const bool visc = s->cfg.eta != 0.0;
-  const bool cfl2 = cfl_in_step && !visc && s->cfg.cooling == GX_COOL_NONE;   // nothing may touch u after the stage for its CFL to stand
+  const bool cfl2 = cfl_in_step && !visc && s->cfg.cooling == GX_COOL_NONE && s->cfg.th_cond == GX_TC_OFF;   // nothing may touch u after the stage for its CFL to stand
   double* full = visc ? s->T : s->U;
   { LaunchScope ls(s, gx::KC_STAGE2); rc = K->stage(A, 2, dt_cfl, s->UP, s->U, full, s->E, s->kz, &s->dscal->dtmin_bits, cfl2 && !A.flux_cd, &s->dscal->err, s->stream); } if (rc) return fail(rc, "stage-2 launch");
   if (A.flux_cd) {
@@ -859,6 +933,7 @@ static int tstep_enqueue_fused(gx_solver* s, double dt_cfl) {
   if (s->cfg.cooling == GX_COOL_H) launch_coolingh(s, dt_cfl);                  // coolingh :202-204
   rc = apply_boundaries(s, s->U, neq, 1, 0, true); if (rc) return rc;           // boundaryI :216
   rc = apply_user_bc(s, s->U, 1); if (rc) return rc;
+  if (s->cfg.th_cond != GX_TC_OFF) { rc = thermal_conduction(s, dt_cfl); if (rc) return rc; }      // :227
   if (!cfl2) {
     LaunchScope ls(s, gx::KC_PRIM);
     K->calcprim(A, s->U, nullptr, nullptr, &s->dscal->dtmin_bits, 1, s->stream);
@@ -916,7 +991,7 @@ static int tstep_enqueue_fused_overlap(gx_solver* s, double dt_cfl) {
 }
 
 static int tstep_enqueue(gx_solver* s, double dt_cfl) {
-  if (s->fused && s->overlap && s->cfg.eta == 0.0 && s->cfg.cooling == GX_COOL_NONE && !s->cfg.bc_user) return tstep_enqueue_fused_overlap(s, dt_cfl);
+  if (s->fused && s->overlap && s->cfg.eta == 0.0 && s->cfg.cooling == GX_COOL_NONE && s->cfg.th_cond == GX_TC_OFF && !s->cfg.bc_user) return tstep_enqueue_fused_overlap(s, dt_cfl);
   if (s->fused) return tstep_enqueue_fused(s, dt_cfl);
   const gx::KernelTable* K = s->K;
   const StepArgs& A = s->A;
@@ -949,6 +1024,11 @@ static int tstep_enqueue(gx_solver* s, double dt_cfl) {
   }
   if (s->cfg.cooling == GX_COOL_H) launch_coolingh(s, dt_cfl);            // coolingh :202-204
   rc = finish_u(s); if (rc) return rc;                                    // boundaryI :216, calcprim :218-224
+  if (s->cfg.th_cond != GX_TC_OFF) {                                      // thermal_conduction :227 (ends with calcprim(u, primit))
+    rc = thermal_conduction(s, dt_cfl); if (rc) return rc;
+    rc = reset_dtmin(s); if (rc) return rc;
+    { LaunchScope ls(s, gx::KC_PRIM); K->calcprim(A, s->U, s->W, nullptr, &s->dscal->dtmin_bits, 1, s->stream); }
+  }
   CUDA_TRY(cudaGetLastError());
   return GX_OK;
 }
@@ -1150,6 +1230,13 @@ int gx_comm_attach(gx_solver* s, const void* idp, int32_t nbytes, int32_t rank, 
     }
     cudaFree(d_ok); cudaFree(d_pk);
   }
+  return GX_OK;
+}
+
+int gx_tc_info(const gx_solver* s, double* dt_cond, int32_t* nsteps) {
+  if (!s) return fail(GX_EINVAL, "null argument");
+  if (dt_cond) *dt_cond = s->tc_dt_cond;
+  if (nsteps) *nsteps = s->tc_nsteps;
   return GX_OK;
 }
 

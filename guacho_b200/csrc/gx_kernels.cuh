@@ -49,7 +49,7 @@ struct StepArgs {
 };
 
 // classes for the per-kernel timing table (gx_kernel_time_ms)
-enum { KC_FLUX = 0, KC_UPDATE = 1, KC_EFIELD = 2, KC_PRIM = 3, KC_BC = 4, KC_XPOSE = 5, KC_VISC = 6, KC_STAGE1 = 7, KC_STAGE2 = 8, KC_BUPDATE = 9, KC_COUNT = 10 };
+enum { KC_FLUX = 0, KC_UPDATE = 1, KC_EFIELD = 2, KC_PRIM = 3, KC_BC = 4, KC_XPOSE = 5, KC_VISC = 6, KC_STAGE1 = 7, KC_STAGE2 = 8, KC_BUPDATE = 9, KC_TCOND = 10, KC_COUNT = 11 };
 
 // One set of launchers per build flavour.
 struct KernelTable {

@@ -116,6 +116,13 @@ module guacho_gpu
       type(c_ptr), value :: handle
       real(c_double), intent(out) :: up(*)
     end function
+    !> thermal conduction log line (src/thermal_cond.f90:723-726): dt_cond in seconds, substeps of the last gx_tstep
+    integer(c_int) function gx_tc_info(handle, dt_cond, nsteps) bind(C, name="gx_tc_info")
+      import :: c_int, c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: handle
+      real(c_double), intent(out) :: dt_cond
+      integer(c_int32_t), intent(out) :: nsteps
+    end function
     !> impose_user_bc as a device functor: wind spheres (EXO/exoplanet.f90:125-266)
     integer(c_int) function gx_set_wind_spheres(handle, n, sph) bind(C, name="gx_set_wind_spheres")
       import :: c_int, c_int32_t, c_ptr, gx_wind_sphere

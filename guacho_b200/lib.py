@@ -22,12 +22,12 @@ ERRORS = {-1: "GX_EINVAL", -2: "GX_ENODEVICE", -3: "GX_ECUDA", -4: "GX_ENOMEM",
 EXPORTS = (
     "gx_create", "gx_destroy", "gx_set_state", "gx_set_time", "gx_get_timestep", "gx_tstep", "gx_run",
     "gx_get_state", "gx_get_up", "gx_set_gravity_points", "gx_set_wind_spheres", "gx_register_host_bc", "gx_register_bc_hook",
-    "gx_register_host_source",
+    "gx_register_host_source", "gx_tc_info",
     "gx_comm_unique_id", "gx_comm_attach", "gx_last_error", "gx_launch_count", "gx_last_elapsed_ms",
     "gx_kernel_time_ms", "gx_set_profiling", "gx_build_info", "gx_riemann_flux",
 )
 
-KERNEL_CLASSES = ("flux", "update", "efield", "prim", "bc", "xpose", "visc", "stage1", "stage2", "bupdate")
+KERNEL_CLASSES = ("flux", "update", "efield", "prim", "bc", "xpose", "visc", "stage1", "stage2", "bupdate", "tcond")
 
 
 class GxError(RuntimeError):
@@ -76,6 +76,7 @@ def load() -> C.CDLL:
     L.gx_register_host_bc.argtypes = [vp, HOST_BC_FN, vp]
     L.gx_register_bc_hook.argtypes = [vp, BC_HOOK_FN, vp]
     L.gx_register_host_source.argtypes = [vp, HOST_SOURCE_FN, vp]
+    L.gx_tc_info.argtypes = [vp, dp, C.POINTER(C.c_int32)]
     L.gx_comm_unique_id.argtypes = [vp, C.c_int32]
     L.gx_comm_attach.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32]
     L.gx_last_error.restype = C.c_char_p

@@ -225,6 +225,12 @@ class Block:
         check(self.L.gx_comm_attach(self.h, buf, 128, rank, nranks))
 
     # -- diagnostics --
+    def tc_info(self):
+        """(dt_cond [s], substeps) of the last step's thermal conduction — the reference's thermal_conduction.log line."""
+        dt, n = C.c_double(0.0), C.c_int32(0)
+        self._check(self.L.gx_tc_info(self.h, C.byref(dt), C.byref(n)))
+        return dt.value, n.value
+
     @property
     def launch_count(self) -> int:
         return int(self.L.gx_launch_count(self.h))

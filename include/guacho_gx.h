@@ -203,6 +203,10 @@ GX_API int gx_comm_attach(gx_solver* s, const void* id, int32_t nbytes, int32_t 
  * functions as the sweeps of gx_tstep (no CPU fallback). */
 GX_API int gx_riemann_flux(const gx_config* cfg, int32_t n, const double* wl, const double* wr, double* ff, int32_t* err);
 
+/* What the reference writes to logs/thermal_conduction.log per call (src/thermal_cond.f90:723-726): the conduction
+ * time scale in seconds (get_dt_cond, :78-110) and the number of substeps of the last gx_tstep.  Zero when th_cond = 0. */
+GX_API int gx_tc_info(const gx_solver* s, double* dt_cond, int32_t* nsteps);
+
 /* ---- diagnostics ---- */
 GX_API const char* gx_last_error(void);
 /* number of kernels of this library launched since gx_create (bench evidence) */

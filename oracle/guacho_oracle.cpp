@@ -54,6 +54,8 @@ struct Par {
   bool bc_user;
   double dx, dy, dz, cv, gamma, Tempsc, cfl, eta;
   int cooling; double tsc;        // parameters.f90: cooling, tsc
+  int th_cond; bool tc_saturation;                 // parameters.f90:117-119
+  double rsc, rhosc, vsc2, vsc, Psc, bsc, mu;      // parameters.f90:159-170 (vsc = sqrt(vsc2), Psc = rhosc*vsc2)
   int nxmin, nxmax, nymin, nymax, nzmin, nzmax;   // parameters.f90:222-227
 };
 
@@ -99,6 +101,8 @@ struct Oracle {
   double RSW, TSW, VSW, dsw, RsS, bsw, bpw, RPW, TPW, VPW, dpw, torb, rorb, omegap, MassS, MassP, xp, yp, zp;
   double exo_rsc = 1, exo_vsc2 = 1;
   bool error_flag = false;
+  // thermal conduction log (what the reference writes to logs/thermal_conduction.log, thermal_cond.f90:725)
+  double tc_dt_cond = 0.0; int tc_nsteps = 0;
 };
 
 static inline double sign1(double x) { return std::copysign(1.0, x); }   // Fortran sign(1.,x), SURVEY Q11
@@ -951,6 +955,195 @@ static void coolingh(Oracle& O, double dt_CFL) {
   });
 }
 
+// ---------------------------------------------------------------------------
+// src/thermal_cond.f90 — thermal conduction, operator-split at the end of tstep (hydro_solver.f90:227).
+// Arithmetic notes: `T**(2.5)` is a call to pow(); integer powers `x**n` are gfortran's __builtin_powi
+// (libgcc __powidf2: binary exponentiation, restated in tc_powi); `**2`/`**3` expand to products.
+// Heat fluxes live in the 5th component of the global f, g, h arrays, in cgs.
+static const double TC_ph = 0.4, TC_nu = 0.01, TC_tstep_red_factor = 0.25;      // thermal_cond.f90:35-40
+static const double TC_Rg = 8.3145e7;                                            // constants.f90:35
+static const double TC_clight = 3.E10;                                           // local parameter, thermal_cond.f90:193,282
+static double tc_powi(double x, int m) {
+  unsigned n = m < 0 ? (unsigned)(-m) : (unsigned)m;
+  double y = (n % 2) ? x : 1.0;
+  while (n >>= 1) { x = x * x; if (n % 2) y *= x; }
+  return m < 0 ? 1.0 / y : y;
+}
+static double tc_Ksp(double T) { return 6.e-7 * std::pow(T, 2.5); }                                   // :142-149
+static double tc_Ksp_parl(double T) { return 9.2181e-7 * std::pow(T, 2.5); }                          // :157-164
+static double tc_Ksp_perp(double T, double dens, double B2) { return 0.30089e+33 * dens / (B2 * std::sqrt(T)) * dens; }   // :172-178
+static inline size_t tc_tix(const Arr4& u, int i, int j, int k) { return (size_t)(i + 1) + (size_t)u.NX * ((size_t)(j + 1) + (size_t)u.NY * (size_t)(k + 1)); }
+
+// thermal_cond.f90:78-110 get_dt_cond
+static double tc_get_dt_cond(Oracle& O) {
+  const Par& P = O.P;
+  std::vector<double> dts(O.B.size(), 0.0);
+  double ddx = std::min(P.dx, P.dy);
+  ddx = std::min(ddx, P.dz);
+  for_blocks(O, [&](Block& b) {
+    double dtp = 1.7976931348623157e308;                                // huge(1.)
+    for (int k = 1; k <= P.nz; ++k) for (int j = 1; j <= P.ny; ++j) for (int i = 1; i <= P.nx; ++i)
+      dtp = std::min(dtp, b.primit(1, i, j, k) / tc_Ksp(b.Temp[tc_tix(b.u, i, j, k)]));     // :95
+    dtp = TC_tstep_red_factor * 0.5 * ((ddx * P.rsc) * (ddx * P.rsc)) * P.cv * TC_Rg * dtp * P.rhosc / P.mu;   // :101
+    dts[b.rank] = dtp;
+  });
+  double dt = dts[0];
+  for (double v : dts) dt = std::min(dt, v);                             // :104 mpi_allreduce(MIN)
+  return dt;
+}
+
+// thermal_cond.f90:189-267 heatfluxes
+static void tc_heatfluxes(const Par& P, Block& b) {
+  const double yhp = 1.;                                                  // :200
+  auto T = [&](int i, int j, int k) { return b.Temp[tc_tix(b.u, i, j, k)]; };
+  auto one = [&](int i, int j, int k, int i2, int j2, int k2, double dxx) -> double {
+    if (T(i, j, k) == T(i2, j2, k2)) return 0.;
+    const double meanP = 0.5 * (b.primit(5, i, j, k) + b.primit(5, i2, j2, k2));
+    const double meanDens = 0.5 * (b.primit(1, i, j, k) + b.primit(1, i2, j2, k2));
+    const double meanT = 0.5 * (T(i, j, k) + T(i2, j2, k2));
+    const double dT = (T(i2, j2, k2) - T(i, j, k)) / (dxx * P.rsc);
+    double coef;
+    if (P.tc_saturation) {
+      double cs = csound(P, meanP, meanDens);
+      cs = std::min(cs * std::sqrt(P.vsc2), TC_clight);
+      coef = std::min(tc_Ksp(meanT), 5. * TC_ph * cs * meanP * P.Psc / std::fabs(dT));
+    } else coef = tc_Ksp(meanT);
+    return -coef * dT * yhp;
+  };
+  for (int k = 0; k <= P.nz; ++k) for (int j = 0; j <= P.ny; ++j) for (int i = 0; i <= P.nx; ++i) {
+    b.f(5, i, j, k) = one(i, j, k, i + 1, j, k, P.dx);
+    b.g(5, i, j, k) = one(i, j, k, i, j + 1, k, P.dy);
+    b.h(5, i, j, k) = one(i, j, k, i, j, k + 1, P.dz);
+  }
+}
+
+// thermal_cond.f90:277-487 MHD_heatfluxes
+static void tc_mhd_heatfluxes(const Par& P, Block& b) {
+  const double phi = 0.3, alpha = 5.0 * phi;
+  auto T = [&](int i, int j, int k) { return b.Temp[tc_tix(b.u, i, j, k)]; };
+  for (size_t n = 4; n < b.f.d.size(); n += (size_t)b.f.n1) { b.f.d[n] = 0.0; b.g.d[n] = 0.0; b.h.d[n] = 0.0; }     // :298
+  for (int k = 0; k <= P.nz; ++k) for (int j = 0; j <= P.ny; ++j) for (int i = 0; i <= P.nx; ++i) {
+    double bx = b.primit(6, i, j, k), by = b.primit(7, i, j, k), bz = b.primit(8, i, j, k);
+    const double B2 = bx * bx + by * by + bz * bz;
+    const double modB = std::sqrt(B2);
+    bx = bx / modB; by = by / modB; bz = bz / modB;
+    double grad[3], Kparl[3], Kperp[3], coefSat[3];
+    const int nb[3][3] = {{i + 1, j, k}, {i, j + 1, k}, {i, j, k + 1}};
+    const double dd[3] = {P.dx, P.dy, P.dz};
+    for (int d = 0; d < 3; ++d) {
+      const int i2 = nb[d][0], j2 = nb[d][1], k2 = nb[d][2];
+      if (std::fabs(T(i, j, k) - T(i2, j2, k2)) < 1.0e-14) { grad[d] = 0.0; Kparl[d] = 0.0; Kperp[d] = 0.0; coefSat[d] = 0.0; continue; }
+      const double meanDens = 0.5 * (b.primit(1, i, j, k) + b.primit(1, i2, j2, k2));
+      const double meanTemp = 0.5 * (T(i, j, k) + T(i2, j2, k2));
+      if (P.tc_saturation) {                                               // :398-403
+        const double meanPres = 0.5 * (b.primit(5, i, j, k) + b.primit(5, i2, j2, k2));
+        double cs = csound(P, meanPres, meanDens);
+        cs = std::min(cs * P.vsc, TC_clight);
+        coefSat[d] = alpha * meanDens * (cs * cs * cs);
+      } else coefSat[d] = 0.0;
+      grad[d] = (T(i2, j2, k2) - T(i, j, k)) / (dd[d] * P.rsc);
+      Kparl[d] = tc_Ksp_parl(meanTemp);
+      Kperp[d] = tc_Ksp_perp(meanTemp, meanDens * P.rhosc, B2 * (P.bsc * P.bsc));
+    }
+    const double bgradT = bx * grad[0] + by * grad[1] + bz * grad[2];     // :370, :458
+    const double parl[3] = {bgradT * bx, bgradT * by, bgradT * bz};
+    const double perp[3] = {grad[0] - parl[0], grad[1] - parl[1], grad[2] - parl[2]};
+    double fl[3];
+    if (!P.tc_saturation) {
+      for (int d = 0; d < 3; ++d) fl[d] = -Kparl[d] * parl[d] - Kperp[d] * perp[d];        // :380-384
+    } else {
+      const double gradT_parl = bgradT;                                    // :464 (signed, as in the reference)
+      const double gradT_perp = std::sqrt(perp[0] * perp[0] + perp[1] * perp[1] + perp[2] * perp[2]);
+      for (int d = 0; d < 3; ++d)                                          // :472-479
+        fl[d] = -1. / (1. / (Kparl[d] + 1.e-14) + gradT_parl / (coefSat[d] + 1.e-14)) * parl[d]
+                - 1. / (1. / (Kperp[d] + 1.e-14) + gradT_perp / (coefSat[d] + 1.e-14)) * perp[d];
+    }
+    b.f(5, i, j, k) = fl[0]; b.g(5, i, j, k) = fl[1]; b.h(5, i, j, k) = fl[2];
+  }
+}
+
+// thermal_cond.f90:496-616 thermal_bounds (MPI branch): one layer of u(5) between blocks, all six faces packed before any is
+// written; then zero-gradient copies on EVERY face of the domain, whatever its boundary type (:589-614) — with periodic
+// boundaries they overwrite what the periodic neighbour sent.
+static void tc_thermal_bounds(Oracle& O) {
+  const Par& P = O.P;
+  const int nx = P.nx, ny = P.ny, nz = P.nz, nxp1 = nx + 1, nyp1 = ny + 1, nzp1 = nz + 1;
+  auto pack5 = [](const Arr4& A, std::vector<double>& buf, int i0, int i1, int j0, int j1, int k0, int k1) {
+    buf.resize((size_t)(i1 - i0 + 1) * (j1 - j0 + 1) * (k1 - k0 + 1));
+    size_t p = 0;
+    for (int k = k0; k <= k1; ++k) for (int j = j0; j <= j1; ++j) for (int i = i0; i <= i1; ++i) buf[p++] = A(5, i, j, k);
+  };
+  auto unpack5 = [](Arr4& A, const std::vector<double>& buf, int i0, int i1, int j0, int j1, int k0, int k1) {
+    size_t p = 0;
+    for (int k = k0; k <= k1; ++k) for (int j = j0; j <= j1; ++j) for (int i = i0; i <= i1; ++i) A(5, i, j, k) = buf[p++];
+  };
+  for_blocks(O, [&](Block& b) {                                           // :514-519
+    pack5(b.u, b.sendr, nx, nx, 0, nyp1, 0, nzp1);
+    pack5(b.u, b.sendl, 1, 1, 0, nyp1, 0, nzp1);
+    pack5(b.u, b.sendt, 0, nxp1, ny, ny, 0, nzp1);
+    pack5(b.u, b.sendb, 0, nxp1, 1, 1, 0, nzp1);
+    pack5(b.u, b.sendi, 0, nxp1, 0, nyp1, nz, nz);
+    pack5(b.u, b.sendo, 0, nxp1, 0, nyp1, 1, 1);
+  });
+  for_blocks(O, [&](Block& b) {                                           // :545-550
+    if (b.left != -1)   unpack5(b.u, O.B[b.left].sendr, 0, 0, 0, nyp1, 0, nzp1);
+    if (b.right != -1)  unpack5(b.u, O.B[b.right].sendl, nxp1, nxp1, 0, nyp1, 0, nzp1);
+    if (b.bottom != -1) unpack5(b.u, O.B[b.bottom].sendt, 0, nxp1, 0, 0, 0, nzp1);
+    if (b.top != -1)    unpack5(b.u, O.B[b.top].sendb, 0, nxp1, nyp1, nyp1, 0, nzp1);
+    if (b.out != -1)    unpack5(b.u, O.B[b.out].sendi, 0, nxp1, 0, nyp1, 0, 0);
+    if (b.in != -1)     unpack5(b.u, O.B[b.in].sendo, 0, nxp1, 0, nyp1, nzp1, nzp1);
+    if (b.coords[0] == 0)         copy_plane(b.u, 0, 0, 1, 0, nyp1, 0, nzp1, 5, 5, 1.);        // :592-614
+    if (b.coords[0] == P.NBX - 1) copy_plane(b.u, 0, nxp1, nx, 0, nyp1, 0, nzp1, 5, 5, 1.);
+    if (b.coords[1] == 0)         copy_plane(b.u, 1, 0, 1, 0, nxp1, 0, nzp1, 5, 5, 1.);
+    if (b.coords[1] == P.NBY - 1) copy_plane(b.u, 1, nyp1, ny, 0, nxp1, 0, nzp1, 5, 5, 1.);
+    if (b.coords[2] == 0)         copy_plane(b.u, 2, 0, 1, 0, nxp1, 0, nyp1, 5, 5, 1.);
+    if (b.coords[2] == P.NBZ - 1) copy_plane(b.u, 2, nzp1, nz, 0, nxp1, 0, nyp1, 5, 5, 1.);
+  });
+}
+
+// thermal_cond.f90:625-636 superstep, :646-654 substep, :664-681 ST_steps
+static double tc_superstep(int N, double snu) {
+  return (double)N / (2. * snu) * (tc_powi(1 + snu, 2 * N) - tc_powi(1 - snu, 2 * N)) / (tc_powi(1 + snu, 2 * N) + tc_powi(1 - snu, 2 * N));
+}
+static double tc_substep(int j, int N, double nu) {
+  const double pi = std::acos(-1.);
+  return 1. / ((nu - 1.) * std::cos(pi * (double)(2 * j - 1) / (2. * (double)N)) + nu + 1.);
+}
+static void tc_ST_steps(double fs, int& Ns, double& fstep) {
+  const double snu = std::sqrt(TC_nu);
+  int j;
+  for (j = 1; j <= 199; ++j) if (tc_superstep(j, snu) > fs) break;       // a completed Fortran do loop leaves j = jmax + 1
+  Ns = j;
+  fstep = fs / tc_superstep(Ns, snu);
+}
+
+// thermal_cond.f90:690-768 thermal_conduction
+static void thermal_conduction(Oracle& O, double dt_CFL) {
+  const Par& P = O.P;
+  const double dt_hydro = dt_CFL * P.tsc;
+  const double dt_cond = tc_get_dt_cond(O);
+  bool SuperStep = true;
+  int Nsteps; double fstep;
+  if (dt_cond < dt_hydro) tc_ST_steps(dt_hydro / dt_cond, Nsteps, fstep);
+  else { SuperStep = false; fstep = dt_hydro / dt_cond; Nsteps = 1; }
+  O.tc_dt_cond = dt_cond; O.tc_nsteps = Nsteps;
+  for (int n = 1; n <= Nsteps; ++n) {
+    double dts;
+    if (SuperStep) dts = dt_cond * fstep * tc_substep(n, Nsteps, TC_nu) / P.Psc / P.rsc;   // :732
+    else dts = dt_hydro / (double)Nsteps / P.Psc / P.rsc;
+    for_blocks(O, [&](Block& b) {
+      if (P.th_cond == GX_TC_ANISOTROPIC) tc_mhd_heatfluxes(P, b);
+      if (P.th_cond == GX_TC_ISOTROPIC) tc_heatfluxes(P, b);
+      for (int k = 1; k <= P.nz; ++k) for (int j = 1; j <= P.ny; ++j) for (int i = 1; i <= P.nx; ++i)      // :749-757
+        b.u(5, i, j, k) = b.u(5, i, j, k) - dts * ((b.f(5, i, j, k) - b.f(5, i - 1, j, k)) / P.dx
+                                                + (b.g(5, i, j, k) - b.g(5, i, j - 1, k)) / P.dy
+                                                + (b.h(5, i, j, k) - b.h(5, i, j, k - 1)) / P.dz);
+    });
+    tc_thermal_bounds(O);                                                // :761
+    for_blocks(O, [&](Block& b) { calcprim(P, b.u, b.primit, b.Temp); });   // :764
+  }
+}
+
 // src/hydro_solver.f90:134-229 tstep  (hydro/MHD part + COOL_H; the other operator-split add-ons are out of scope)
 static int tstep(Oracle& O, double dt_CFL) {
   const Par& P = O.P;
@@ -966,6 +1159,7 @@ static int tstep(Oracle& O, double dt_CFL) {
   if (P.cooling == GX_COOL_H) coolingh(O, dt_CFL);                      // :202-204
   boundaryI(O);                                                         // :216
   for_blocks(O, [&](Block& b) { calcprim(P, b.u, b.primit, b.Temp); }); // :218-220 (cooling NONE/H branch)
+  if (P.th_cond != 0) thermal_conduction(O, dt_CFL);                    // :227
   if (err) O.error_flag = true;
   return err;
 }
@@ -1165,6 +1359,8 @@ static Oracle* create(const gx_config& c) {
   P.bc_user = c.bc_user;
   P.dx = c.dx; P.dy = c.dy; P.dz = c.dz; P.cv = c.cv; P.gamma = c.gamma; P.Tempsc = c.Tempsc; P.cfl = c.cfl; P.eta = c.eta;
   P.cooling = c.cooling; P.tsc = c.tsc;
+  P.th_cond = c.th_cond; P.tc_saturation = c.tc_saturation != 0;
+  P.rsc = c.rsc; P.rhosc = c.rhosc; P.vsc2 = c.vsc2; P.vsc = std::sqrt(c.vsc2); P.Psc = c.rhosc * c.vsc2; P.bsc = c.bsc; P.mu = c.mu;
   P.nxmin = -1; P.nxmax = P.nx + 2; P.nymin = -1; P.nymax = P.ny + 2; P.nzmin = -1; P.nzmax = P.nz + 2;
   const bool perx = (P.bc_left == GX_BC_PERIODIC && P.bc_right == GX_BC_PERIODIC);    // src/init.f90:64-66
   const bool pery = (P.bc_bottom == GX_BC_PERIODIC && P.bc_top == GX_BC_PERIODIC);
@@ -1311,6 +1507,13 @@ double orc_cfastX(void* h, const double* prim) { return orc::cfastX(((Oracle*)h)
 void orc_cool_atomic(void* h, double dt_seconds, double* uu) { orc::cool_atomic(((Oracle*)h)->P, dt_seconds, uu); }
 double orc_cool_rate(int which, double T) { return which == 0 ? orc::cool_alpha(T) : which == 1 ? orc::cool_colf(T) : orc::cool_betah(T); }
 double orc_cool_aloss(double x1, double x2, double dt, double den, double dh0, double te) { return orc::cool_aloss(x1, x2, dt, den, dh0, te); }
+// thermal conduction: what the reference logs per call (dt_cond in seconds, number of substeps), and the pieces for KATs
+void orc_tc_info(void* h, double* dt_cond, int* nsteps) { Oracle* O = (Oracle*)h; *dt_cond = O->tc_dt_cond; *nsteps = O->tc_nsteps; }
+void orc_thermal_conduction(void* h, double dt_cfl) { orc::thermal_conduction(*(Oracle*)h, dt_cfl); }
+double orc_tc_superstep(int n) { return orc::tc_superstep(n, std::sqrt(orc::TC_nu)); }
+double orc_tc_substep(int j, int n) { return orc::tc_substep(j, n, orc::TC_nu); }
+void orc_tc_st_steps(double fs, int* ns, double* fstep) { orc::tc_ST_steps(fs, *ns, *fstep); }
+double orc_tc_ksp(int which, double T, double dens, double B2) { return which == 0 ? orc::tc_Ksp(T) : which == 1 ? orc::tc_Ksp_parl(T) : orc::tc_Ksp_perp(T, dens, B2); }
 double orc_csound(void* h, double p, double d) { return orc::csound(((Oracle*)h)->P, p, d); }
 
 }  // extern "C"

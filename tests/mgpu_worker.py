@@ -3,8 +3,9 @@
 Every rank advances its block of a decomposed domain through the C ABI (NCCL halo exchange and
 CFL all-reduce inside libguacho_gx.so); rank 0 also advances the same problem as ONE block and
 checks that the gathered interiors are bitwise equal (G-GPU == 1-GPU).
-usage: mgpu_worker.py NBX NBY NBZ NX NY NZ NSTEPS PROBLEM [strict] [outflowz] [eta] [oracle]
+usage: mgpu_worker.py NBX NBY NBZ NX NY NZ NSTEPS PROBLEM [strict] [outflowz] [eta] [oracle] [tcond]
   eta    : eta = 0.01 (viscous_copy reads up's stale half-step ghosts, SURVEY Q5: the reference itself depends on the decomposition)
+  tcond  : isotropic saturated thermal conduction (src/thermal_cond.f90) with several super-time-stepping substeps per step, outflow walls
   oracle : compare with the CPU oracle run on the SAME block grid (1e-12 relative per variable; bitwise with `strict`) instead of one GPU block
 """
 import os
@@ -40,6 +41,11 @@ def main():
     kw = dict(bc_out=BC_OUTFLOW, bc_in=BC_OUTFLOW) if outflowz else {}
     if with_eta:
         kw["eta"] = 0.01
+    if "tcond" in sys.argv[9:]:
+        from guacho_b200.config import TC_ISOTROPIC
+        from tests.util import tc_scalings
+        kw.update(th_cond=TC_ISOTROPIC, tc_saturation=True, bc_left=BC_OUTFLOW, bc_right=BC_OUTFLOW, bc_bottom=BC_OUTFLOW, bc_top=BC_OUTFLOW,
+                  bc_out=BC_OUTFLOW, bc_in=BC_OUTFLOW, **tc_scalings(rhosc=1e-18))
     p = Params(nxtot=nx, nytot=ny, nztot=nz, zmax=1.0, strict_fp=strict, **kw)
     nb = (nbx, nby, nbz)
     blk = make_rank_block(p, rank, world, local_rank, nb=nb)
@@ -57,6 +63,8 @@ def main():
         dts.append(dt)
         t += dt
         it += 1
+    if p.th_cond:
+        assert blk.tc_info()[1] > 1, blk.tc_info()          # the super-time-stepping schedule ran
     mine = np.ascontiguousarray(blk.interior(blk.get_state()))
     gathered = [None] * world
     dist.all_gather_object(gathered, (coords, mine, dts))

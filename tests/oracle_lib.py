@@ -89,6 +89,15 @@ def load(fast: bool = False):
     L.orc_cool_rate.argtypes = [C.c_int, C.c_double]
     L.orc_cool_aloss.restype = C.c_double
     L.orc_cool_aloss.argtypes = [C.c_double] * 6
+    L.orc_tc_info.argtypes = [C.c_void_p, dp, ip]
+    L.orc_thermal_conduction.argtypes = [C.c_void_p, C.c_double]
+    L.orc_tc_superstep.restype = C.c_double
+    L.orc_tc_superstep.argtypes = [C.c_int]
+    L.orc_tc_substep.restype = C.c_double
+    L.orc_tc_substep.argtypes = [C.c_int, C.c_int]
+    L.orc_tc_st_steps.argtypes = [C.c_double, ip, dp]
+    L.orc_tc_ksp.restype = C.c_double
+    L.orc_tc_ksp.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
     _libs[name] = L
     return L
 
@@ -190,6 +199,16 @@ class Oracle:
     def tstep(self, dt: float) -> int:
         self.L.orc_set_time(self.h, self.time)
         return self.L.orc_tstep(self.h, dt)
+
+    def thermal_conduction(self, dt_cfl: float) -> None:
+        """thermal_conduction() of src/thermal_cond.f90:690-768 alone (primit/Temp must be current: start())."""
+        self.L.orc_thermal_conduction(self.h, dt_cfl)
+
+    def tc_info(self):
+        """(dt_cond [s], substeps) of the last thermal_conduction call — the reference's log line (:725)."""
+        dt, n = C.c_double(0.0), C.c_int(0)
+        self.L.orc_tc_info(self.h, C.byref(dt), C.byref(n))
+        return dt.value, n.value
 
     def advance(self, nsteps: int, n_iter: int = 10, tprint: float = 1e300):
         """main.f90:94-125 without output."""

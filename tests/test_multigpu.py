@@ -82,3 +82,13 @@ def test_two_gpu_y_blocks_viscosity_matches_the_oracle_on_the_same_blocks():
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     _run((1, 2, 1), (48, 40, 32), 3, "random", strict=True, port=29549, extra=("eta", "oracle"))
+
+
+@pytest.mark.parametrize("nb,port", [((1, 1, 2), 29550), ((1, 2, 1), 29551)])
+def test_two_gpu_thermal_conduction_matches_the_oracle_on_the_same_blocks(nb, port):
+    """Thermal conduction (src/thermal_cond.f90) on two GPUs: the conduction time scale is a global minimum (mpi_allreduce,
+    :104), every substep exchanges one layer of u(5) alone (thermal_bounds, :496-616) — z slabs through the peer-memory push
+    of a single variable, y blocks through pack / NCCL / unpack."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run(nb, (32, 24, 24), 3, "random", port=port, extra=("tcond", "oracle"))

@@ -39,3 +39,14 @@ def rel_err_per_var(a: np.ndarray, ref: np.ndarray) -> np.ndarray:
 
 def interior(a: np.ndarray) -> np.ndarray:
     return a[..., 2:-2, 2:-2, 2:-2]
+
+
+def tc_scalings(rhosc: float = 1e-15, **kw) -> dict:
+    """cgs scalings for the thermal-conduction tests (pattern of parameters.f90:152-170): a hot (1e6 K), thin plasma in a box
+    of 1e10 cm, for which the Spitzer time scale of a ~16-cell grid is comparable to the hydro step (rhosc = 1e-15) or well
+    below it (smaller rhosc: super-time-stepping with several substeps)."""
+    mu, Rg, gamma, T0, rsc = 0.6, 8.3145e7, 5.0 / 3.0, 1.0e6, 1e10
+    vsc2 = gamma * Rg * T0 / mu
+    d = dict(rsc=rsc, rhosc=rhosc, vsc2=vsc2, tsc=rsc / np.sqrt(vsc2), bsc=float(np.sqrt(4 * np.pi * rhosc * vsc2)), mu=mu, Tempsc=T0 * gamma)
+    d.update(kw)
+    return d
