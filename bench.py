@@ -289,6 +289,61 @@ def run_exo(args, rank, local_rank, world):
     return 0
 
 
+def run_tcond(args, rank, local_rank, world):
+    """the headline workload with the thermal-conduction operator on (src/thermal_cond.f90: isotropic Spitzer
+    conduction with saturation, super-time-stepping), one GPU.  Reports the whole step and the operator's own HBM fraction."""
+    import torch
+    from guacho_b200.config import TC_ISOTROPIC
+    from guacho_b200.solver import Block
+    if world != 1:
+        raise SystemExit("--problem tcond runs on one GPU")
+    mu, Rg, gamma, T0, rsc, rhosc = 0.6, 8.3145e7, 5.0 / 3.0, 1.0e6, 1e10, 2e-17
+    vsc2 = gamma * Rg * T0 / mu
+    p = workload(args.n, 1, False, "hlld").replace(strict_fp=args.strict, device=local_rank, th_cond=TC_ISOTROPIC, tc_saturation=True, rsc=rsc, rhosc=rhosc,
+                                                    vsc2=vsc2, tsc=rsc / np.sqrt(vsc2), bsc=float(np.sqrt(4 * np.pi * rhosc * vsc2)), mu=mu, Tempsc=T0 * gamma)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    with Block(p) as blk:
+        blk.set_state(problems.orszag_tang(p, (0, 0, 0)))
+        tsim, it, _ = blk.run(max(3, args.warmup), 0.0, 11)           # past the CFL ramp: the hydro step is long against the conduction time scale
+        torch.cuda.synchronize()
+        l0, tw0 = blk.launch_count, time.time()
+        tsim, it, last_dt = blk.run(args.steps, tsim, it)
+        tw1, l1 = time.time(), blk.launch_count
+        ms = blk.last_elapsed_ms
+        clocks = sampler.stop(tw0, tw1)
+        dt_cond, nsub = blk.tc_info()
+        blk.set_profiling(True)
+        nprof = min(args.steps, 3)
+        sub = 0
+        for _ in range(nprof):
+            tsim, it, _ = blk.run(1, tsim, it)
+            sub += blk.tc_info()[1]
+        ktimes = blk.kernel_times()
+        blk.set_profiling(False)
+        finite = bool(np.isfinite(blk.get_state()).all())
+    peak_gbs, peak_src = measured_peaks()
+    zones = p.nx * p.ny * p.nz
+    step_ms = ms / args.steps
+    tc_ms = ktimes["tcond"][0] / nprof
+    # per substep: k_tc_update reads p, T, rho and reads + writes u(5) (5 doubles); k_tc_prim reads the 8 dynamic variables and
+    # writes p, T (10 doubles); the first k_tc_prim of a call (dt_cond) replaces the one after the last substep
+    tc_bytes = (40.0 + 80.0) * zones * (sub / nprof)
+    line = {"metric": "MHD zone-updates/s with thermal conduction (HLLD + flux-CD + isotropic saturated Spitzer conduction, super-time-stepping, FP64)",
+            "value": zones * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"3D Orszag-Tang {args.n}^3 HLLD+flux-CD + th_cond=ISOTROPIC, tc_saturation (thermal_cond.f90), periodic box", "grid_total": [p.nxtot, p.nytot, p.nztot],
+                       "substeps_last_step": nsub, "dt_cond_s": dt_cond, "l2": "working set exceeds the 126 MB L2; no flush needed"},
+            "clocks": clocks, "gpu_launches": int(l1 - l0),
+            "roofline": {"bound": "hbm", "achieved": tc_bytes / (tc_ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s", "frac": tc_bytes / (tc_ms * 1e-3) / 1e9 / peak_gbs, "traffic": None,
+                         "peak_source": peak_src, "kernel": "k_tc_update + k_tc_prim (thermal conduction substeps)", "ms_per_step": tc_ms,
+                         "substeps_per_step": sub / nprof, "algorithmic_bytes_per_zone_per_substep": 120.0,
+                         "kernel_ms_per_step": {k: v[0] / nprof for k, v in ktimes.items() if v[1]}},
+            "finite": finite, "last_dt": last_dt}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -301,7 +356,8 @@ def main():
     ap.add_argument("--strict", action="store_true", help="use the -fmad=false bit-comparison kernels")
     ap.add_argument("--solver", default="hlld", choices=sorted(SOLVERS), help="Riemann solver (BASELINE configs[4] sweep); the headline metric is hlld")
     ap.add_argument("--strong", action="store_true", help="strong scaling: --n is the TOTAL grid side, split into z-slabs over the GPUs")
-    ap.add_argument("--problem", default="ot", choices=["ot", "exo"], help="ot: the headline workload; exo: EXO/ as shipped (BASELINE configs[3]), 400x100x400, one GPU")
+    ap.add_argument("--problem", default="ot", choices=["ot", "exo", "tcond"],
+                    help="ot: the headline workload; exo: EXO/ as shipped (BASELINE configs[3]), 400x100x400, one GPU; tcond: ot with the thermal-conduction operator on")
     ap.add_argument("--no-extras", action="store_true", help="skip the 512^3 lines (extra.grid512 at N=1; extra.weak512 / extra.strong512 at N>1)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -322,6 +378,8 @@ def main():
 
     if args.problem == "exo":
         return run_exo(args, rank, local_rank, world)
+    if args.problem == "tcond":
+        return run_tcond(args, rank, local_rank, world)
     if args.strong and args.n % world:
         raise SystemExit(f"--strong: {args.n} planes do not split over {world} GPUs")
     p = workload(args.n, world, args.strong, args.solver).replace(strict_fp=args.strict)

@@ -12,6 +12,7 @@ from dataclasses import dataclass, field, asdict
 
 # ---- named constants, values identical to src/constants.f90:56-98 ----
 SOLVER_HLL, SOLVER_HLLC, SOLVER_HLLE, SOLVER_HLLD = 1, 2, 3, 4
+SOLVER_HLLE_SPLIT_ALL = 7            # src/constants.f90:62 (HLLE on fluctuations about a background state, src/hlle_split_all.f90)
 EOS_ADIABATIC, EOS_SINGLE_SPECIE, EOS_H_RATE, EOS_CHEM = 1, 2, 3, 4
 TC_OFF, TC_ISOTROPIC, TC_ANISOTROPIC = 0, 1, 2
 BC_OUTFLOW, BC_CLOSED, BC_PERIODIC, BC_OTHER = 1, 2, 3, 4
@@ -19,7 +20,7 @@ COOL_NONE, COOL_H = 0, 1
 LIMITER_NO_AVERAGE, LIMITER_NO_LIMIT, LIMITER_MINMOD, LIMITER_VAN_LEER = -1, 0, 1, 2
 LIMITER_VAN_ALBADA, LIMITER_UMIST, LIMITER_WOODWARD, LIMITER_SUPERBEE = 3, 4, 5, 6
 
-SOLVER_NAMES = {SOLVER_HLL: "HLL", SOLVER_HLLC: "HLLC", SOLVER_HLLE: "HLLE", SOLVER_HLLD: "HLLD"}
+SOLVER_NAMES = {SOLVER_HLL: "HLL", SOLVER_HLLC: "HLLC", SOLVER_HLLE: "HLLE", SOLVER_HLLD: "HLLD", SOLVER_HLLE_SPLIT_ALL: "HLLE_SPLIT_ALL"}
 ALL_LIMITERS = (LIMITER_NO_AVERAGE, LIMITER_NO_LIMIT, LIMITER_MINMOD, LIMITER_VAN_LEER,
                 LIMITER_VAN_ALBADA, LIMITER_UMIST, LIMITER_WOODWARD, LIMITER_SUPERBEE)
 
@@ -155,7 +156,7 @@ class Params:
             raise ValueError("grid is not divisible by the block decomposition")
         if min(self.nx, self.ny, self.nz) < NGHOST:
             raise ValueError("each block needs at least nghost=2 cells per direction")
-        if self.riemann_solver in (SOLVER_HLLE, SOLVER_HLLD) and not self.mhd:
+        if self.riemann_solver in (SOLVER_HLLE, SOLVER_HLLD, SOLVER_HLLE_SPLIT_ALL) and not self.mhd:
             raise ValueError("HLLE/HLLD need mhd=True (they use cfastX)")
         if self.riemann_solver in (SOLVER_HLL, SOLVER_HLLC) and self.mhd:
             raise ValueError("HLL/HLLC use the hydro sound speed: run them with mhd=False")

@@ -78,6 +78,7 @@ struct gx_solver {
   cudaEvent_t ev_bnd = nullptr, ev_comm = nullptr;
   bool overlap = false;                                       // z slabs + peer push: boundary-first launches, exchange on cstream
   double *U = nullptr, *UP = nullptr, *W = nullptr, *F = nullptr, *E = nullptr, *Temp = nullptr, *T = nullptr;
+  double* W0 = nullptr;                                       // split-all solver: background primitives (gx_set_background)
   double* PT = nullptr;                                       // thermal conduction: pressure and temperature (2 variables)
   double tc_dt_cond = 0.0; int tc_nsteps = 0;                 // what the reference logs per call (thermal_cond.f90:725)
   double* stage = nullptr; size_t stage_doubles = 0;         // AoS staging for layout conversion
@@ -637,7 +638,14 @@ int gx_create(const gx_config* c, gx_solver** out) {
   if (c->pmhd) return fail(GX_EUNSUPPORTED, "passive-MHD (pmhd) is not implemented on the device path");
   const bool mhd_solver = c->riemann_solver == GX_SOLVER_HLLE || c->riemann_solver == GX_SOLVER_HLLD;
   const bool hd_solver = c->riemann_solver == GX_SOLVER_HLL || c->riemann_solver == GX_SOLVER_HLLC;
-  if (!mhd_solver && !hd_solver) return fail(GX_EUNSUPPORTED, "riemann_solver %d not implemented (split variants have no reference implementation either)", c->riemann_solver);
+  const bool split_solver = c->riemann_solver == GX_SOLVER_HLLE_SPLIT_ALL;
+  if (!mhd_solver && !hd_solver && !split_solver)
+    return fail(GX_EUNSUPPORTED, "riemann_solver %d not implemented (the SPLIT_B variants and HLLD_SPLIT_ALL have no reference implementation either: "
+                                 "hydro_solver.f90:159-162 calls none of them)", c->riemann_solver);
+  if (split_solver && !(c->mhd && c->neqdyn == 8 && c->npas == 0 && (c->eq_of_state == GX_EOS_ADIABATIC || c->eq_of_state == GX_EOS_SINGLE_SPECIE)))
+    return fail(GX_EINVAL, "HLLE_SPLIT_ALL: mhd = 1, neqdyn = 8, no passive scalars (the split flux exists under `if (mhd)` only, hydro_core.f90:404)");
+  if (split_solver && c->cooling != GX_COOL_NONE) return fail(GX_EUNSUPPORTED, "HLLE_SPLIT_ALL with cooling");
+  if (split_solver && c->th_cond != GX_TC_OFF) return fail(GX_EUNSUPPORTED, "HLLE_SPLIT_ALL with thermal conduction");
   if (mhd_solver && !(c->mhd && c->neqdyn == 8)) return fail(GX_EINVAL, "HLLE/HLLD need mhd=1, neqdyn=8");
   if (hd_solver && (c->mhd || c->neqdyn != 5)) return fail(GX_EINVAL, "HLL/HLLC use hydro wave speeds: run with mhd=0, neqdyn=5 (SURVEY Q12)");
   if (c->enable_flux_cd && !c->mhd) return fail(GX_EINVAL, "flux-CD without B field updates nothing (hydro_solver.f90:103-113)");
@@ -675,7 +683,7 @@ int gx_create(const gx_config* c, gx_solver** out) {
   s->A.idx3[0] = 1.0 / c->dx; s->A.idx3[1] = 1.0 / c->dy; s->A.idx3[2] = 1.0 / c->dz;
   s->A.solver = c->riemann_solver; s->A.limiter = c->slope_limiter;
   s->A.flux_cd = c->enable_flux_cd; s->A.eight_wave = c->eight_wave; s->A.user_src = c->user_source_terms;
-  s->A.grav.n = 0;
+  s->A.grav.n = 0; s->A.W0 = nullptr;
   s->A.kbeg = 1; s->A.klast = nz; s->A.kbeg2 = 1; s->A.klast2 = 0;
   s->K = c->strict_fp ? gx::kernels_strict() : gx::kernels_fast();
 
@@ -701,7 +709,7 @@ int gx_create(const gx_config* c, gx_solver** out) {
   // counts and a host-callback source (gx_register_host_source switches this off) take the pass-per-routine kernels.
   const bool fuse_a = c->npas == 0 && !c->user_source_terms && c->eq_of_state == GX_EOS_ADIABATIC;
   const bool fuse_b = c->npas == 2;
-  s->fused = (fuse_a || fuse_b) && !c->eight_wave && !getenv("GX_NO_FUSED");
+  s->fused = (fuse_a || fuse_b) && !c->eight_wave && !split_solver && !getenv("GX_NO_FUSED");
   s->kz = 0;                                        // planes per CTA of the fused stage kernels: chosen by their launcher
   if (const char* e = getenv("GX_KZ")) s->kz = std::max(1, atoi(e));
   // a user boundary functor may write ghost cells, so ghosts must be real arrays then
@@ -721,6 +729,7 @@ int gx_create(const gx_config* c, gx_solver** out) {
   }
   if (c->enable_flux_cd) ALLOC(s->E, var_bytes * 3);
   if (c->th_cond != GX_TC_OFF) ALLOC(s->PT, var_bytes * 2);
+  if (split_solver) ALLOC(s->W0, var_bytes * g.neq);
   ALLOC(s->dscal, sizeof(gx_solver::DevScalars));
   if (cudaMallocHost((void**)&s->hscal, sizeof(gx_solver::DevScalars)) != cudaSuccess) { s->hscal = nullptr; gx_destroy(s); cudaGetLastError(); return fail(GX_ENOMEM, "cudaMallocHost failed (pinned scalars)"); }
   // staging: up to 64 MiB or 4 planes, whichever is larger
@@ -761,7 +770,7 @@ int gx_destroy(gx_solver* s) {
   }
   if (s->flags) cudaFree(s->flags);
   if (s->comm && g_nccl.ok) g_nccl.CommDestroy(s->comm);
-  double* ptrs[] = {s->U, s->UP, s->W, s->F, s->E, s->Temp, s->T, s->PT, s->stage};
+  double* ptrs[] = {s->U, s->UP, s->W, s->F, s->E, s->Temp, s->T, s->PT, s->W0, s->stage};
   for (double* p : ptrs) if (p) cudaFree(p);
   for (int q = 0; q < 6; ++q) { if (s->halo_send[q]) cudaFree(s->halo_send[q]); if (s->halo_recv[q]) cudaFree(s->halo_recv[q]); }
   if (s->dscal) cudaFree(s->dscal);
@@ -866,8 +875,21 @@ static int finish_u(gx_solver* s) {
   return GX_OK;
 }
 
+int gx_set_background(gx_solver* s, const double* primit0) {
+  if (!s || !primit0) return fail(GX_EINVAL, "null argument");
+  if (s->cfg.riemann_solver != GX_SOLVER_HLLE_SPLIT_ALL) return fail(GX_EINVAL, "gx_set_background: riemann_solver is not HLLE_SPLIT_ALL");
+  cudaSetDevice(s->device);
+  int rc = upload_aos(s, primit0, s->W0, s->A.g.neq); if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  collect_timed(s);
+  s->A.W0 = s->W0;
+  return GX_OK;
+}
+
 int gx_set_state(gx_solver* s, const double* u) {
   if (!s || !u) return fail(GX_EINVAL, "null argument");
+  if (s->cfg.riemann_solver == GX_SOLVER_HLLE_SPLIT_ALL && !s->A.W0)
+    return fail(GX_ESTATE, "HLLE_SPLIT_ALL: call gx_set_background (primit0) before gx_set_state — u holds fluctuations about it");
   cudaSetDevice(s->device);
   int rc = upload_aos(s, u, s->U, s->A.g.neq); if (rc) return rc;
   rc = reset_scalars(s); if (rc) return rc;

@@ -10,6 +10,7 @@
 //                 src/flux_cd_module.f90:285-323, src/sources.f90:124-220
 //   k_viscous   : viscous_copy  src/hydro_solver.f90:47-65
 #include "gx_kernels.cuh"
+#include "gx_split.cuh"
 
 #if defined(GX_FLAVOUR_STRICT)
 #define GX_NS strict_ns
@@ -84,6 +85,36 @@ __global__ void __launch_bounds__(128) k_calcprim(const StepArgs A, const double
   if (want_cfl) block_atomic_min(dtp, dtmin_bits);
 }
 
+// calcprim of the split-all solver: u2primSplitAll (src/hydro_core.f90:143-229, called at :263-309) and the CFL candidates of
+// the TOTAL state (:650-654).  u, W: fluctuations; W0: background primitives.
+__global__ void __launch_bounds__(128) k_calcprim_split(const StepArgs A, const double* __restrict__ U, double* __restrict__ W,
+                                                        double* __restrict__ Temp, unsigned long long* dtmin_bits, int want_cfl) {
+  const Grid& g = A.g;
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) - 1;
+  const int j = (int)blockIdx.y - 1, k = (int)blockIdx.z - 1;
+  double dtp = 1.e30;
+  if (i <= g.nx + 2) {
+    const long long c = g.idx(i, j, k);
+    double u[8], w0[8], w[8], T;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { u[q] = U[q * g.vs + c]; w0[q] = A.W0[q * g.vs + c]; }
+    gxp::u2prim_split(A.phys, u, w0, w, T);
+    if (W) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) W[q * g.vs + c] = w[q];
+    }
+    if (Temp) Temp[c] = T;
+    if (want_cfl && i >= 1 && i <= g.nx && j >= 1 && j <= g.ny && k >= 1 && k <= g.nz) {
+      double cx, cy, cz;
+      gxp::cfast3(A.phys, w[4] + w0[4], w[0] + w0[0], w[5] + w0[5], w[6] + w0[6], w[7] + w0[7], cx, cy, cz);
+      dtp = fmin(dtp, g.dx / (fabs(w[1]) + cx));
+      dtp = fmin(dtp, g.dy / (fabs(w[2]) + cy));
+      dtp = fmin(dtp, g.dz / (fabs(w[3]) + cz));
+    }
+  }
+  if (want_cfl) block_atomic_min(dtp, dtmin_bits);
+}
+
 // ---------------------------------------------------------------------------
 // storage component of rotated slot c for sweep direction D (swapy / swapz as an index map)
 template <int D> __device__ __forceinline__ constexpr int comp(int c) {
@@ -127,6 +158,32 @@ __global__ void __launch_bounds__(128, GX_FLUX_MINBLOCKS) k_flux(const StepArgs 
     if (ORDER == 2) gxp::reconstruct<LIM>(Wq[-st], pl, pr, Wq[2 * st]);
     Fd[(long long)q * g.vs] = gxp::passive_flux(I, pl, pr);
   }
+}
+
+// hllEfluxesSplitAll(choice) (src/hlle_split_all.f90:97-241): the sweep of k_flux with the background states alongside; the
+// limiter acts on the fluctuations and on the background separately (:154-155).
+template <int LIM, int ORDER, int D>
+__global__ void __launch_bounds__(128) k_flux_split(const StepArgs A, const double* __restrict__ W, double* __restrict__ F) {
+  const Grid& g = A.g;
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) + (D == 0 ? 0 : 1);
+  const int j = (int)blockIdx.y + (D == 1 ? 0 : 1);
+  const int k = (int)blockIdx.z + (D == 2 ? 0 : 1);
+  if (i > g.nx) return;
+  const long long st = (D == 0) ? 1 : (D == 1) ? (long long)g.px : (long long)g.px * g.py;
+  const long long c = g.idx(i, j, k);
+  double wl[8], wr[8], w0l[8], w0r[8], ff[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const double* Wq = W + (long long)comp<D>(q) * g.vs + c;
+    const double* Bq = A.W0 + (long long)comp<D>(q) * g.vs + c;
+    double pl = Wq[0], pr = Wq[st], bl = Bq[0], br = Bq[st];
+    if (ORDER == 2) { gxp::reconstruct<LIM>(Wq[-st], pl, pr, Wq[2 * st]); gxp::reconstruct<LIM>(Bq[-st], bl, br, Bq[2 * st]); }
+    wl[q] = pl; wr[q] = pr; w0l[q] = bl; w0r[q] = br;
+  }
+  gxp::riemann_hlle_split_all(A.phys, wl, wr, w0l, w0r, ff);
+  double* Fd = F + (long long)D * g.neq * g.vs + c;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) Fd[(long long)comp<D>(q) * g.vs] = ff[q];
 }
 
 // ---------------------------------------------------------------------------
@@ -367,7 +424,8 @@ static inline dim3 grid_for(int nxr, int nyr, int nzr, int bx) { return dim3((un
 static void l_calcprim(const StepArgs& A, const double* U, double* W, double* Temp, unsigned long long* dtmin_bits, int want_cfl, cudaStream_t s) {
   const Grid& g = A.g;
   dim3 grid = grid_for(g.nx + 4, g.ny + 4, g.nz + 4, 128);
-  if (A.phys.neqdyn == 8) k_calcprim<true><<<grid, 128, 0, s>>>(A, U, W, Temp, dtmin_bits, want_cfl);
+  if (A.solver == GX_SOLVER_HLLE_SPLIT_ALL) k_calcprim_split<<<grid, 128, 0, s>>>(A, U, W, Temp, dtmin_bits, want_cfl);
+  else if (A.phys.neqdyn == 8) k_calcprim<true><<<grid, 128, 0, s>>>(A, U, W, Temp, dtmin_bits, want_cfl);
   else k_calcprim<false><<<grid, 128, 0, s>>>(A, U, W, Temp, dtmin_bits, want_cfl);
 }
 
@@ -395,8 +453,32 @@ static int l_flux_solver(const StepArgs& A, int order, const double* W, double* 
   return GX_EINVAL;
 }
 
+template <int LIM, int ORDER>
+static void l_flux3_split(const StepArgs& A, const double* W, double* F, cudaStream_t s) {
+  const Grid& g = A.g;
+  k_flux_split<LIM, ORDER, 0><<<grid_for(g.nx + 1, g.ny, g.nz, 128), 128, 0, s>>>(A, W, F);
+  k_flux_split<LIM, ORDER, 1><<<grid_for(g.nx, g.ny + 1, g.nz, 128), 128, 0, s>>>(A, W, F);
+  k_flux_split<LIM, ORDER, 2><<<grid_for(g.nx, g.ny, g.nz + 1, 128), 128, 0, s>>>(A, W, F);
+}
+static int l_flux_split(const StepArgs& A, int order, const double* W, double* F, cudaStream_t s) {
+  if (!A.W0) return GX_ESTATE;
+  if (order == 1) { l_flux3_split<GX_LIMITER_NO_AVERAGE, 1>(A, W, F, s); return 0; }
+  switch (A.limiter) {
+    case GX_LIMITER_NO_AVERAGE: l_flux3_split<GX_LIMITER_NO_AVERAGE, 2>(A, W, F, s); return 0;
+    case GX_LIMITER_NO_LIMIT:   l_flux3_split<GX_LIMITER_NO_LIMIT, 2>(A, W, F, s); return 0;
+    case GX_LIMITER_MINMOD:     l_flux3_split<GX_LIMITER_MINMOD, 2>(A, W, F, s); return 0;
+    case GX_LIMITER_VAN_LEER:   l_flux3_split<GX_LIMITER_VAN_LEER, 2>(A, W, F, s); return 0;
+    case GX_LIMITER_VAN_ALBADA: l_flux3_split<GX_LIMITER_VAN_ALBADA, 2>(A, W, F, s); return 0;
+    case GX_LIMITER_UMIST:      l_flux3_split<GX_LIMITER_UMIST, 2>(A, W, F, s); return 0;
+    case GX_LIMITER_WOODWARD:   l_flux3_split<GX_LIMITER_WOODWARD, 2>(A, W, F, s); return 0;
+    case GX_LIMITER_SUPERBEE:   l_flux3_split<GX_LIMITER_SUPERBEE, 2>(A, W, F, s); return 0;
+  }
+  return GX_EINVAL;
+}
+
 static int l_fluxes(const StepArgs& A, int order, const double* W, double* F, int* errflag, cudaStream_t s) {
   switch (A.solver) {
+    case GX_SOLVER_HLLE_SPLIT_ALL: return l_flux_split(A, order, W, F, s);
     case GX_SOLVER_HLL:  return l_flux_solver<GX_SOLVER_HLL>(A, order, W, F, errflag, s);
     case GX_SOLVER_HLLC: return l_flux_solver<GX_SOLVER_HLLC>(A, order, W, F, errflag, s);
     case GX_SOLVER_HLLE: return l_flux_solver<GX_SOLVER_HLLE>(A, order, W, F, errflag, s);

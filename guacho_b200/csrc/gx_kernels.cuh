@@ -46,6 +46,7 @@ struct StepArgs {
   int solver, limiter;
   int flux_cd, eight_wave, user_src;
   GravityPoints grav;
+  const double* W0;        // background primitives of the split-all solver (src/globals.f90:42 primit0; gx_set_background), else null
 };
 
 // classes for the per-kernel timing table (gx_kernel_time_ms)

@@ -115,6 +115,9 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, int parity) {
 #ifndef GX_STAGE_TYP                 // tile rows of the kernels that carry passive scalars (more variables per staged cell)
 #define GX_STAGE_TYP 7
 #endif
+#ifndef GX_STAGE_MINB1               // resident CTAs per SM the first-order headline kernel is compiled for (register cap = 64 K / threads)
+#define GX_STAGE_MINB1 1
+#endif
 #ifndef GX_STAGE_NPAS                // passive scalars of the second set of fused kernels (EXO: neutral H density + tracer)
 #define GX_STAGE_NPAS 2
 #endif
@@ -194,7 +197,7 @@ struct StageTraits {
 // u2prim with the run-time equation of state (EOS_H_RATE reads the first passive) and adds the point-mass gravity functor
 // of get_user_source_terms in the update — EXO as shipped leaves the pass-per-routine path.
 template <int SOLVER, int LIM, int ORDER, bool FLUXCD, int NPAS, bool TMA>
-__global__ void __launch_bounds__((StageTraits<SOLVER, LIM, ORDER, FLUXCD, NPAS>::G::NT), 1)
+__global__ void __launch_bounds__((StageTraits<SOLVER, LIM, ORDER, FLUXCD, NPAS>::G::NT), (ORDER == 1 && NPAS == 0) ? GX_STAGE_MINB1 : 1)
 k_stage(const StepArgs A, const StageDt sdt, const double* __restrict__ S, const double* Ub, double* dst,
         double* __restrict__ E, const int kz, unsigned long long* dtmin_bits, const int want_cfl, int* errflag,
         const __grid_constant__ CUtensorMap tmS) {

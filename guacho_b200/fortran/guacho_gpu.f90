@@ -52,6 +52,12 @@ module guacho_gpu
       import :: c_int, c_ptr
       type(c_ptr), value :: handle
     end function
+    !> primit0 of SOLVER_HLLE_SPLIT_ALL (globals.f90:42, init.f90:153-154): background primitives; before gx_set_state
+    integer(c_int) function gx_set_background(handle, primit0) bind(C, name="gx_set_background")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value         :: handle
+      real(c_double), intent(in) :: primit0(*)
+    end function
     !> initflow -> boundaryI -> calcprim  (main.f90:73-79)
     integer(c_int) function gx_set_state(handle, u) bind(C, name="gx_set_state")
       import :: c_int, c_ptr, c_double

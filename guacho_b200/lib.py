@@ -20,7 +20,7 @@ ERRORS = {-1: "GX_EINVAL", -2: "GX_ENODEVICE", -3: "GX_ECUDA", -4: "GX_ENOMEM",
 
 # every symbol include/guacho_gx.h declares (checked by tests/test_abi.py)
 EXPORTS = (
-    "gx_create", "gx_destroy", "gx_set_state", "gx_set_time", "gx_get_timestep", "gx_tstep", "gx_run",
+    "gx_create", "gx_destroy", "gx_set_background", "gx_set_state", "gx_set_time", "gx_get_timestep", "gx_tstep", "gx_run",
     "gx_get_state", "gx_get_up", "gx_set_gravity_points", "gx_set_wind_spheres", "gx_register_host_bc", "gx_register_bc_hook",
     "gx_register_host_source", "gx_tc_info",
     "gx_comm_unique_id", "gx_comm_attach", "gx_last_error", "gx_launch_count", "gx_last_elapsed_ms",
@@ -64,6 +64,7 @@ def load() -> C.CDLL:
     vp = C.c_void_p
     L.gx_create.argtypes = [C.POINTER(GxConfig), C.POINTER(vp)]
     L.gx_destroy.argtypes = [vp]
+    L.gx_set_background.argtypes = [vp, dp]
     L.gx_set_state.argtypes = [vp, dp]
     L.gx_set_time.argtypes = [vp, C.c_double]
     L.gx_get_timestep.argtypes = [vp, C.c_int32, C.c_int32, C.c_double, C.c_double, dp, C.POINTER(C.c_int32)]

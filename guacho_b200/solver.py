@@ -92,6 +92,13 @@ class Block:
     def empty_state(self) -> np.ndarray:
         return np.zeros(self.shape, dtype=np.float64, order="F")
 
+    def set_background(self, primit0: np.ndarray) -> None:
+        """primit0 of the split-all solver (src/globals.f90:42): background primitives, same shape as u; before set_state."""
+        if primit0.shape != self.shape:
+            raise ValueError(f"primit0 has shape {primit0.shape}, expected {self.shape}")
+        a = np.asfortranarray(primit0, dtype=np.float64)
+        self._check(self.L.gx_set_background(self.h, _dp(a)))
+
     # -- calls main.f90 makes --
     def set_state(self, u: np.ndarray) -> None:
         """initflow -> boundaryI -> calcprim (main.f90:73-79)."""

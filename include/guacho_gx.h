@@ -97,6 +97,12 @@ GX_API int gx_create(const gx_config* cfg, gx_solver** out);
 /* Frees all device memory (the reference never deallocates; end of main.f90). */
 GX_API int gx_destroy(gx_solver* s);
 
+/* Replaces: the host filling `primit0` (src/globals.f90:42, allocated at src/init.f90:153-154) — the background
+ * primitives of SOLVER_HLLE_SPLIT_ALL (src/hlle_split_all.f90:51-241; u2primSplitAll, src/hydro_core.f90:143-229).
+ * Same layout as gx_set_state's array; u then holds FLUCTUATIONS about it (totals: src/Out_BIN_Module.f90:144-156).
+ * Must precede gx_set_state.  The reference ships no problem that uses this solver and marks its energy flux "REVISAR". */
+GX_API int gx_set_background(gx_solver* s, const double* primit0);
+
 /* Replaces initflow -> boundaryI -> calcprim at start-up (src/main.f90:73-79):
  * `u` is the caller-owned conserved array in reference layout WITH ghosts.
  * The library uploads it, converts to SoA, and applies boundaryI semantics. */

@@ -84,6 +84,7 @@ struct Block {
   int coords[3];
   int left, right, bottom, top, out, in;   // src/init.f90:108-110 ; -1 = MPI_PROC_NULL
   Arr4 u, up, primit, f, g, h, e;          // src/globals.f90:33-39, flux_cd_module.f90:35
+  Arr4 primit0;                            // src/globals.f90:42 (split-all solvers only: background primitives, set by the host)
   std::vector<double> Temp;                // (nxmin:nxmax, nymin:nymax, nzmin:nzmax)
   // halo buffers (src/boundaries.f90:56-58, 271-273)
   std::vector<double> sendr, sendl, sendt, sendb, sendi, sendo;
@@ -139,11 +140,45 @@ static void u2prim(const Par& P, const double* uu, double* prim, double& T) {
   }
 }
 
+static inline bool split_all(const Par& P) { return P.riemann_solver == GX_SOLVER_HLLE_SPLIT_ALL || P.riemann_solver == GX_SOLVER_HLLD_SPLIT_ALL; }
+
+// src/hydro_core.f90:143-229  u2primSplitAll: uu and prim are FLUCTUATIONS about the background prim0; no floors
+static void u2primSplitAll(const Par& P, const double* uu, double* prim, const double* prim0, double& T) {
+  prim[0] = uu[0];                                                      // :159
+  double r = prim[0] + prim0[0];                                        // :161
+  prim[1] = uu[1] / r;
+  prim[2] = uu[2] / r;
+  prim[3] = uu[3] / r;
+  if (P.mhd || P.pmhd) { prim[5] = uu[5]; prim[6] = uu[6]; prim[7] = uu[7]; }   // :168-170
+  if (P.mhd) {                                                          // :174-179
+    prim[4] = (uu[4] - 0.5 * r * (prim[1] * prim[1] + prim[2] * prim[2] + prim[3] * prim[3])
+                     - 0.5 * (uu[5] * uu[5] + uu[6] * uu[6] + uu[7] * uu[7])
+                     - prim0[5] * uu[5] - prim0[6] * uu[6] - prim0[7] * uu[7]) / P.cv;
+  } else {
+    prim[4] = (uu[4] - 0.5 * r * (prim[1] * prim[1] + prim[2] * prim[2] + prim[3] * prim[3])) / P.cv;
+  }
+  if (P.passives) for (int q = P.neqdyn; q < P.neq; ++q) prim[q] = uu[q];       // :187-189
+  T = 0.0;
+  if (P.eq_of_state == GX_EOS_ADIABATIC) T = ((prim[4] + prim0[4]) / r) * P.Tempsc;          // :194-196
+  if (P.eq_of_state == GX_EOS_SINGLE_SPECIE) {                                                // :198-203
+    r = std::max(r, 1e-15);
+    T = std::max(1., ((prim[4] + prim0[4]) / r) * P.Tempsc);
+  }
+  if (P.passives && P.eq_of_state == GX_EOS_H_RATE) {                                         // :207-212
+    double dentot = (2. * r - prim[P.neqdyn] - prim0[P.neqdyn]);
+    dentot = std::max(dentot, 1e-15);
+    T = std::max(1., ((prim[4] + prim0[4]) / dentot) * P.Tempsc);
+  }
+}
+
 // src/hydro_core.f90:245-320  calcprim
-static void calcprim(const Par& P, const Arr4& u, Arr4& primit, std::vector<double>& Temp, bool only_ghost = false) {
+static void calcprim(const Par& P, const Arr4& u, Arr4& primit, std::vector<double>& Temp, bool only_ghost = false, const Arr4* primit0 = nullptr) {
   const int NX = u.NX, NY = u.NY;
   auto tix = [&](int i, int j, int k) { return (size_t)(i + 1) + (size_t)NX * ((size_t)(j + 1) + (size_t)NY * (size_t)(k + 1)); };
-  auto one = [&](int i, int j, int k) { u2prim(P, u.cell(i, j, k), primit.cell(i, j, k), Temp[tix(i, j, k)]); };
+  auto one = [&](int i, int j, int k) {
+    if (split_all(P)) u2primSplitAll(P, u.cell(i, j, k), primit.cell(i, j, k), primit0->cell(i, j, k), Temp[tix(i, j, k)]);   // :263-266, 307-309
+    else u2prim(P, u.cell(i, j, k), primit.cell(i, j, k), Temp[tix(i, j, k)]);
+  };
   if (only_ghost) {                                                     // :258-301
     for (int j = 0; j <= P.ny + 1; ++j) for (int i = 0; i <= P.nx + 1; ++i) { one(i, j, 0); one(i, j, P.nz + 1); }
     for (int k = 0; k <= P.nz + 1; ++k) for (int i = 0; i <= P.nx + 1; ++i) { one(i, 0, k); one(i, P.ny + 1, k); }
@@ -556,6 +591,93 @@ static int fluxes(const Par& P, Block& b, int choice) {
         std::memcpy(b.h.cell(i, j, k), ff, sizeof(double) * neq);
       }
   return err;
+}
+
+// ---------------------------------------------------------------------------
+// HLLE with every variable split into background + fluctuation (src/hlle_split_all.f90; marked unfinished upstream: "REVISAR")
+// src/hydro_core.f90:340-368  prim2u, split branch (prim0 present)
+static void prim2u_split(const Par& P, const double* prim, const double* prim0, double* uu) {
+  uu[0] = prim[0];
+  uu[1] = prim[1] * (prim[0] + prim0[0]);
+  uu[2] = prim[2] * (prim[0] + prim0[0]);
+  uu[3] = prim[3] * (prim[0] + prim0[0]);
+  uu[4] = 0.5 * prim[0] * (prim[1] * prim[1] + prim[2] * prim[2] + prim[3] * prim[3]) + P.cv * prim[4];   // :356
+  if (P.mhd) {                                                          // :362-364
+    uu[4] = uu[4] + 0.5 * (prim[5] * prim[5] + prim[6] * prim[6] + prim[7] * prim[7])
+                  + 0.5 * prim0[0] * (prim[1] * prim[1] + prim[2] * prim[2] + prim[3] * prim[3])
+                  + prim0[5] * prim[5] + prim0[6] * prim[6] + prim0[7] * prim[7];
+  }
+  if (P.mhd || P.pmhd) { uu[5] = prim[5]; uu[6] = prim[6]; uu[7] = prim[7]; }
+  if (P.passives) for (int q = P.neqdyn; q < P.neq; ++q) uu[q] = prim[q];
+}
+// src/hydro_core.f90:404-427, 457-461  prim2f, split branch (mhd, prim0 present)
+static void prim2f_split(const Par& P, const double* prim, const double* prim0, double* ff) {
+  const double rt = prim[0] + prim0[0];
+  const double etot = 0.5 * (rt * (prim[1] * prim[1] + prim[2] * prim[2] + prim[3] * prim[3])
+                             + prim[5] * prim[5] + prim[6] * prim[6] + prim[7] * prim[7])
+                      + P.cv * prim[4]
+                      + prim0[5] * prim[5] + prim0[6] * prim[6] + prim0[7] * prim[7];
+  ff[0] = rt * prim[1];
+  ff[1] = rt * prim[1] * prim[1] + prim[4] + 0.5 * (prim[6] * prim[6] + prim[7] * prim[7] - prim[5] * prim[5])
+          - prim0[5] * prim[5] + prim0[6] * prim[6] + prim0[7] * prim[7];
+  ff[2] = rt * prim[1] * prim[2] - prim[5] * prim[6]
+          - prim0[6] * prim[5] - prim0[5] * prim[6];
+  ff[3] = rt * prim[1] * prim[3] - prim[5] * prim[7]
+          - prim0[7] * prim[5] - prim0[5] * prim[7];
+  ff[4] = prim[1] * (etot + prim[4] + 0.5 * ((prim[5] + prim0[5]) * (prim[5] + prim0[5]) + (prim[6] + prim0[6]) * (prim[6] + prim0[6])
+                                              + (prim[7] + prim0[7]) * (prim[7] + prim0[7]))
+                     + P.cv * prim0[4] + prim0[4] + 0.5 * (prim0[5] * prim0[5] + prim0[6] * prim0[6] + prim0[7] * prim0[7]))
+          - (prim[5] + prim0[5]) * (prim[1] * (prim[5] + prim0[5]) + prim[2] * (prim[6] + prim0[6]) + prim[3] * (prim[7] + prim0[7]));
+  ff[5] = 0.;
+  ff[6] = prim[1] * (prim0[6] + prim[6]) - prim[2] * (prim0[5] + prim[5]);
+  ff[7] = prim[1] * (prim0[7] + prim[7]) - prim[3] * (prim0[5] + prim[5]);
+  if (P.passives) for (int q = P.neqdyn; q < P.neq; ++q) ff[q] = prim[q] * prim[1];
+}
+// src/hlle_split_all.f90:51-85  prim2fhlleSplitAll
+static void prim2fhlleSplitAll(const Par& P, const double* priml, const double* primr, const double* prim0l, const double* prim0r, double* ff) {
+  double tl[16], tr[16];
+  for (int q = 0; q < P.neq; ++q) { tl[q] = priml[q] + prim0l[q]; tr[q] = primr[q] + prim0r[q]; }
+  const double csl = cfastX(P, tl), csr = cfastX(P, tr);                 // :61-62
+  const double sr = std::max(priml[1] + prim0l[1] + csl, primr[1] + prim0r[1] + csr);
+  const double sl = std::min(priml[1] + prim0l[1] - csl, primr[1] + prim0r[1] - csr);
+  if (sl > 0) { prim2f_split(P, priml, prim0l, ff); return; }
+  if (sr < 0) { prim2f_split(P, primr, prim0r, ff); return; }
+  double fL[16], fR[16], uL[16], uR[16];
+  prim2f_split(P, priml, prim0l, fL);
+  prim2f_split(P, primr, prim0r, fR);
+  prim2u_split(P, priml, prim0l, uL);
+  prim2u_split(P, primr, prim0r, uR);
+  for (int q = 0; q < P.neq; ++q) ff[q] = (sr * fL[q] - sl * fR[q] + sl * sr * (uR[q] - uL[q])) / (sr - sl);   // :83
+}
+// src/hlle_split_all.f90:97-241  hllEfluxesSplitAll(choice): the sweep of `fluxes` with the background states alongside
+// (the limiter is applied to the fluctuations and to the background separately, :154-155)
+static int fluxes_split_all(const Par& P, Block& b, int choice) {
+  const int neq = P.neq;
+  double priml[16], primr[16], primll[16], primrr[16], prim0l[16], prim0r[16], prim0ll[16], prim0rr[16], ff[16];
+  for (int q = 0; q < 16; ++q) ff[q] = 0.0;
+  auto ld = [&](double* dst, const Arr4& A, int i, int j, int k) { std::memcpy(dst, A.cell(i, j, k), sizeof(double) * neq); };
+  const int di[3] = {1, 0, 0}, dj[3] = {0, 1, 0}, dk[3] = {0, 0, 1};
+  Arr4* out[3] = {&b.f, &b.g, &b.h};
+  for (int k = 0; k <= P.nz; ++k)
+    for (int j = 0; j <= P.ny; ++j)
+      for (int i = 0; i <= P.nx; ++i)
+        for (int d = 0; d < 3; ++d) {
+          auto sw = [&](double* v) { if (d == 1) swapy(P, v); if (d == 2) swapz(P, v); };
+          ld(priml, b.primit, i, j, k); ld(primr, b.primit, i + di[d], j + dj[d], k + dk[d]);
+          ld(prim0l, b.primit0, i, j, k); ld(prim0r, b.primit0, i + di[d], j + dj[d], k + dk[d]);
+          sw(priml); sw(primr); sw(prim0l); sw(prim0r);
+          if (choice == 2) {
+            ld(primll, b.primit, i - di[d], j - dj[d], k - dk[d]); ld(primrr, b.primit, i + 2 * di[d], j + 2 * dj[d], k + 2 * dk[d]);
+            ld(prim0ll, b.primit0, i - di[d], j - dj[d], k - dk[d]); ld(prim0rr, b.primit0, i + 2 * di[d], j + 2 * dj[d], k + 2 * dk[d]);
+            sw(primll); sw(primrr); sw(prim0ll); sw(prim0rr);
+            limiter(P.slope_limiter, primll, priml, primr, primrr, neq);
+            limiter(P.slope_limiter, prim0ll, prim0l, prim0r, prim0rr, neq);
+          }
+          prim2fhlleSplitAll(P, priml, primr, prim0l, prim0r, ff);
+          sw(ff);
+          std::memcpy(out[d]->cell(i, j, k), ff, sizeof(double) * neq);
+        }
+  return 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -1140,7 +1262,7 @@ static void thermal_conduction(Oracle& O, double dt_CFL) {
                                                 + (b.h(5, i, j, k) - b.h(5, i, j, k - 1)) / P.dz);
     });
     tc_thermal_bounds(O);                                                // :761
-    for_blocks(O, [&](Block& b) { calcprim(P, b.u, b.primit, b.Temp); });   // :764
+    for_blocks(O, [&](Block& b) { calcprim(P, b.u, b.primit, b.Temp, false, &b.primit0); });   // :764
   }
 }
 
@@ -1149,16 +1271,16 @@ static int tstep(Oracle& O, double dt_CFL) {
   const Par& P = O.P;
   std::atomic<int> err(0);
   double dtm = dt_CFL / 2.;                                             // :152
-  for_blocks(O, [&](Block& b) { err |= fluxes(P, b, 1); });             // :155-161
+  for_blocks(O, [&](Block& b) { err |= split_all(P) ? fluxes_split_all(P, b, 1) : fluxes(P, b, 1); });   // :155-161
   step(O, dtm);                                                         // :165
   boundaryII(O);                                                        // :169
-  for_blocks(O, [&](Block& b) { calcprim(P, b.up, b.primit, b.Temp); });   // :170
-  for_blocks(O, [&](Block& b) { err |= fluxes(P, b, 2); });             // :174-180
+  for_blocks(O, [&](Block& b) { calcprim(P, b.up, b.primit, b.Temp, false, &b.primit0); });   // :170
+  for_blocks(O, [&](Block& b) { err |= split_all(P) ? fluxes_split_all(P, b, 2) : fluxes(P, b, 2); });   // :174-180
   step(O, dt_CFL);                                                      // :184
   viscous_copy(O);                                                      // :188
   if (P.cooling == GX_COOL_H) coolingh(O, dt_CFL);                      // :202-204
   boundaryI(O);                                                         // :216
-  for_blocks(O, [&](Block& b) { calcprim(P, b.u, b.primit, b.Temp); }); // :218-220 (cooling NONE/H branch)
+  for_blocks(O, [&](Block& b) { calcprim(P, b.u, b.primit, b.Temp, false, &b.primit0); }); // :218-220 (cooling NONE/H branch)
   if (P.th_cond != 0) thermal_conduction(O, dt_CFL);                    // :227
   if (err) O.error_flag = true;
   return err;
@@ -1174,6 +1296,10 @@ static void get_timestep(Oracle& O, int current_iter, int n_iter, double current
       const double* p = b.primit.cell(i, j, k);
       if (P.mhd) {
         double cx, cy, cz;
+        if (split_all(P)) {                                             // :650-654
+          const double* p0 = b.primit0.cell(i, j, k);
+          cfast(P, p[4] + p0[4], p[0] + p0[0], p[5] + p0[5], p[6] + p0[6], p[7] + p0[7], cx, cy, cz);
+        } else
         cfast(P, p[4], p[0], p[5], p[6], p[7], cx, cy, cz);
         dtp = std::min(dtp, P.dx / (std::fabs(p[1]) + cx));
         dtp = std::min(dtp, P.dy / (std::fabs(p[2]) + cy));
@@ -1382,6 +1508,7 @@ static Oracle* create(const gx_config& c) {
     b.f.alloc(P.neq, P.nx, P.ny, P.nz); b.g.alloc(P.neq, P.nx, P.ny, P.nz); b.h.alloc(P.neq, P.nx, P.ny, P.nz);
     if (P.enable_flux_cd && P.neqdyn == 8) b.e.alloc(3, P.nx, P.ny, P.nz);
     b.Temp.assign((size_t)(P.nx + 4) * (P.ny + 4) * (P.nz + 4), 0.0);
+    if (split_all(P)) b.primit0.alloc(P.neq, P.nx, P.ny, P.nz);          // src/init.f90:153-154
   }
   return O;
 }
@@ -1406,10 +1533,10 @@ void orc_block_neighbors(void* h, int b, int* n6) {
 void orc_set_time(void* h, double t) { ((Oracle*)h)->time = t; }
 int orc_error(void* h) { return ((Oracle*)h)->error_flag ? 1 : 0; }
 
-// which: 0 u, 1 up, 2 primit, 3 f, 4 g, 5 h, 6 e, 7 Temp
+// which: 0 u, 1 up, 2 primit, 3 f, 4 g, 5 h, 6 e, 7 Temp, 8 primit0
 static orc::Arr4* pick(Oracle* O, int b, int which) {
   orc::Block& B = O->B[b];
-  switch (which) { case 0: return &B.u; case 1: return &B.up; case 2: return &B.primit; case 3: return &B.f; case 4: return &B.g; case 5: return &B.h; case 6: return &B.e; }
+  switch (which) { case 0: return &B.u; case 1: return &B.up; case 2: return &B.primit; case 3: return &B.f; case 4: return &B.g; case 5: return &B.h; case 6: return &B.e; case 8: return &B.primit0; }
   return nullptr;
 }
 int64_t orc_block_array_size(void* h, int which) {
@@ -1452,6 +1579,22 @@ void orc_scatter_u_with_ghosts(void* h, const double* g) {
     }
 }
 
+// split-all solvers: scatter a global background WITH ghosts into every block's primit0 (the host's job in the reference)
+void orc_scatter_primit0_with_ghosts(void* h, const double* g) {
+  Oracle* O = (Oracle*)h; const orc::Par& P = O->P;
+  const size_t GX = P.nxtot + 4, GY = P.nytot + 4;
+  for (auto& B : O->B)
+    for (int k = P.nzmin; k <= P.nzmax; ++k) for (int j = P.nymin; j <= P.nymax; ++j) for (int i = P.nxmin; i <= P.nxmax; ++i) {
+      size_t gi = (size_t)(i + 1 + B.coords[0] * P.nx), gj = (size_t)(j + 1 + B.coords[1] * P.ny), gk = (size_t)(k + 1 + B.coords[2] * P.nz);
+      const double* s = g + (size_t)P.neq * (gi + GX * (gj + GY * gk));
+      double* c = B.primit0.cell(i, j, k);
+      for (int q = 0; q < P.neq; ++q) c[q] = s[q];
+    }
+}
+void orc_riemann_split_all(void* h, const double* pl, const double* pr, const double* p0l, const double* p0r, double* ff) {
+  orc::prim2fhlleSplitAll(((Oracle*)h)->P, pl, pr, p0l, p0r, ff);
+}
+
 void orc_impose_ot(void* h, double rsc) { orc::impose_ot(*(Oracle*)h, rsc); }
 void orc_init_exo(void* h, double rsc, double rhosc, double Tempsc, double vsc2, double tsc, double bsc) {
   Oracle* O = (Oracle*)h; orc::init_exo(*O, rsc, rhosc, Tempsc, vsc2, tsc, bsc); O->builtin_user = 1;
@@ -1468,8 +1611,8 @@ void orc_set_user_source(void* h, orc::user_src_fn fn, void* ctx) { Oracle* O = 
 // the calls main.f90 makes (src/main.f90:73-79, 97, 106)
 void orc_boundaryI(void* h) { orc::boundaryI(*(Oracle*)h); }
 void orc_boundaryII(void* h) { orc::boundaryII(*(Oracle*)h); }
-void orc_calcprim_u(void* h) { Oracle* O = (Oracle*)h; orc::for_blocks(*O, [&](orc::Block& b) { orc::calcprim(O->P, b.u, b.primit, b.Temp); }); }
-void orc_calcprim_up(void* h) { Oracle* O = (Oracle*)h; orc::for_blocks(*O, [&](orc::Block& b) { orc::calcprim(O->P, b.up, b.primit, b.Temp); }); }
+void orc_calcprim_u(void* h) { Oracle* O = (Oracle*)h; orc::for_blocks(*O, [&](orc::Block& b) { orc::calcprim(O->P, b.u, b.primit, b.Temp, false, &b.primit0); }); }
+void orc_calcprim_up(void* h) { Oracle* O = (Oracle*)h; orc::for_blocks(*O, [&](orc::Block& b) { orc::calcprim(O->P, b.up, b.primit, b.Temp, false, &b.primit0); }); }
 void orc_start(void* h) { orc_boundaryI(h); orc_calcprim_u(h); }
 void orc_get_timestep(void* h, int current_iter, int n_iter, double current_time, double tprint, double* dt, int* dump_flag) {
   orc::get_timestep(*(Oracle*)h, current_iter, n_iter, current_time, tprint, *dt, *dump_flag);

@@ -18,7 +18,7 @@ from guacho_b200.config import GxConfig, Params
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
 
-U, UP, PRIMIT, F, G, H, E, TEMP = range(8)
+U, UP, PRIMIT, F, G, H, E, TEMP, PRIMIT0 = range(9)
 
 
 def build_oracle(force: bool = False) -> None:
@@ -89,6 +89,8 @@ def load(fast: bool = False):
     L.orc_cool_rate.argtypes = [C.c_int, C.c_double]
     L.orc_cool_aloss.restype = C.c_double
     L.orc_cool_aloss.argtypes = [C.c_double] * 6
+    L.orc_scatter_primit0_with_ghosts.argtypes = [C.c_void_p, dp]
+    L.orc_riemann_split_all.argtypes = [C.c_void_p, dp, dp, dp, dp, dp]
     L.orc_tc_info.argtypes = [C.c_void_p, dp, ip]
     L.orc_thermal_conduction.argtypes = [C.c_void_p, C.c_double]
     L.orc_tc_superstep.restype = C.c_double
@@ -164,6 +166,18 @@ class Oracle:
         a = np.asfortranarray(g, dtype=np.float64)
         assert a.shape == (p.neq, p.nxtot + 4, p.nytot + 4, p.nztot + 4)
         self.L.orc_scatter_u_with_ghosts(self.h, _dp(a))
+
+    def scatter_primit0(self, g: np.ndarray) -> None:
+        """Background primitives of the split-all solvers (globals primit0, set by the host): global array with ghosts."""
+        p = self.p
+        a = np.asfortranarray(g, dtype=np.float64)
+        assert a.shape == (p.neq, p.nxtot + 4, p.nytot + 4, p.nztot + 4)
+        self.L.orc_scatter_primit0_with_ghosts(self.h, _dp(a))
+
+    def riemann_split_all(self, pl, pr, p0l, p0r):
+        a, b, c, d, out = self._vec(pl), self._vec(pr), self._vec(p0l), self._vec(p0r), np.zeros(16)
+        self.L.orc_riemann_split_all(self.h, _dp(a), _dp(b), _dp(c), _dp(d), _dp(out))
+        return out[:self.p.neq].copy()
 
     def coords(self, b: int):
         c = (C.c_int * 3)()
