@@ -297,7 +297,7 @@ def run_tcond(args, rank, local_rank, world):
     from guacho_b200.solver import Block
     if world != 1:
         raise SystemExit("--problem tcond runs on one GPU")
-    mu, Rg, gamma, T0, rsc, rhosc = 0.6, 8.3145e7, 5.0 / 3.0, 1.0e6, 1e10, 2e-17
+    mu, Rg, gamma, T0, rsc, rhosc = 0.6, 8.3145e7, 5.0 / 3.0, 1.0e6, 1e10, 5e-16
     vsc2 = gamma * Rg * T0 / mu
     p = workload(args.n, 1, False, "hlld").replace(strict_fp=args.strict, device=local_rank, th_cond=TC_ISOTROPIC, tc_saturation=True, rsc=rsc, rhosc=rhosc,
                                                     vsc2=vsc2, tsc=rsc / np.sqrt(vsc2), bsc=float(np.sqrt(4 * np.pi * rhosc * vsc2)), mu=mu, Tempsc=T0 * gamma)

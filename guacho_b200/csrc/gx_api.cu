@@ -18,7 +18,6 @@
 
 #include "../../include/guacho_gx.h"
 #include "gx_kernels.cuh"
-#include "gx_thermal.cuh"
 
 using gx::Grid;
 using gx::StepArgs;
@@ -728,7 +727,7 @@ int gx_create(const gx_config* c, gx_solver** out) {
     ALLOC(s->T, var_bytes * g.neq);                  // full-step state before viscous_copy (up keeps its half-step ghosts)
   }
   if (c->enable_flux_cd) ALLOC(s->E, var_bytes * 3);
-  if (c->th_cond != GX_TC_OFF) ALLOC(s->PT, var_bytes * 2);
+  if (c->th_cond != GX_TC_OFF) ALLOC(s->PT, var_bytes * 2 + 256 * 16 * sizeof(double));    // p, T + the reduction slots of get_dt_cond
   if (split_solver) ALLOC(s->W0, var_bytes * g.neq);
   ALLOC(s->dscal, sizeof(gx_solver::DevScalars));
   if (cudaMallocHost((void**)&s->hscal, sizeof(gx_solver::DevScalars)) != cudaSuccess) { s->hscal = nullptr; gx_destroy(s); cudaGetLastError(); return fail(GX_ENOMEM, "cudaMallocHost failed (pinned scalars)"); }
@@ -806,38 +805,64 @@ static int ensure_array(gx_solver* s, double** p, size_t nvar) {
 }
 
 // ---------------------------------------------------------------------------
+namespace gxtc {
+// ---- host side of thermal_conduction (:625-681): super-time-stepping schedule ----
+// integer powers are gfortran's __builtin_powi (binary exponentiation)
+inline double powi(double x, int m) {
+  unsigned n = m < 0 ? (unsigned)(-m) : (unsigned)m;
+  double y = (n % 2) ? x : 1.0;
+  while (n >>= 1) { x = x * x; if (n % 2) y *= x; }
+  return m < 0 ? 1.0 / y : y;
+}
+inline double superstep(int N, double snu) {
+  return (double)N / (2. * snu) * (powi(1 + snu, 2 * N) - powi(1 - snu, 2 * N)) / (powi(1 + snu, 2 * N) + powi(1 - snu, 2 * N));
+}
+inline double substep(int j, int N, double nu) {
+  const double pi = acos(-1.);
+  return 1. / ((nu - 1.) * cos(pi * (double)(2 * j - 1) / (2. * (double)N)) + nu + 1.);
+}
+inline void ST_steps(double fs, int& Ns, double& fstep) {
+  const double snu = sqrt(0.01);
+  int j;
+  for (j = 1; j <= 199; ++j) if (superstep(j, snu) > fs) break;
+  Ns = j;
+  fstep = fs / superstep(Ns, snu);
+}
+
+}  // namespace gxtc
+
 // thermal_conduction (src/thermal_cond.f90:690-768), called at the end of tstep on u with its ghost layer filled
 // (hydro_solver.f90:216-227).  One host round trip per call: the conduction time scale decides the number of substeps,
 // exactly where the reference does its mpi_allreduce (:104).
 static int thermal_bounds(gx_solver* s) {
   // :496-616 (MPI branch): one layer of u(5) between blocks, then zero-gradient copies on every face of the DOMAIN whatever
   // its boundary type — so a periodic direction owned by one block needs no wrap copy at all (it would be overwritten).
-  double* A = s->U + 4 * s->A.g.vs;
+  const Grid& g = s->A.g;
+  double* A = s->U + 4 * g.vs;
+  int edge = 0;
   for (int dir = 0; dir < 3; ++dir) {
+    for (int side = 0; side < 2; ++side) if (s->co[dir] == (side == 0 ? 0 : s->nb[dir] - 1)) edge |= 1 << (2 * dir + side);
     if (s->nb[dir] == 1) continue;
     int rc = exchange_dir(s, A, 1, 1, dir); if (rc) return rc;
   }
-  for (int dir = 0; dir < 3; ++dir)
-    for (int side = 0; side < 2; ++side)
-      if (s->co[dir] == (side == 0 ? 0 : s->nb[dir] - 1)) launch_bc_face(s, A, 1, dir, side, 1, 1, -1);
+  LaunchScope ls(s, gx::KC_BC);
+  s->K->tc_fill(s->A, A, edge, s->stream);
   return GX_OK;
 }
 static int thermal_conduction(gx_solver* s, double dt_cfl) {
   const Grid& g = s->A.g;
   const gx_config& c = s->cfg;
-  gxtc::TcPar t;
+  gx::TcPar t;
   t.mode = c.th_cond; t.sat = c.tc_saturation; t.mhd = c.mhd;
   t.dxr = c.dx * c.rsc; t.dyr = c.dy * c.rsc; t.dzr = c.dz * c.rsc;
-  t.dx = c.dx; t.dy = c.dy; t.dz = c.dz;
+  t.idxr = 1.0 / t.dxr; t.idyr = 1.0 / t.dyr; t.idzr = 1.0 / t.dzr;
+  t.dx = c.dx; t.dy = c.dy; t.dz = c.dz; t.idx = 1.0 / c.dx; t.idy = 1.0 / c.dy; t.idz = 1.0 / c.dz;
   t.vsc = sqrt(c.vsc2); t.sqrt_vsc2 = sqrt(c.vsc2);
   t.Psc = c.rhosc * c.vsc2; t.rhosc = c.rhosc; t.bsc2 = c.bsc * c.bsc;
-  const dim3 gp((g.nx + 2 + 127) / 128, g.ny + 2, g.nz + 2), gu((g.nx + 127) / 128, g.ny, g.nz);
-  auto prim = [&](int want_dt) {
-    LaunchScope ls(s, gx::KC_TCOND);
-    gxtc::k_tc_prim<<<gp, 128, 0, s->stream>>>(g, s->A.phys, c.mhd, s->U, s->PT, &s->dscal->tc_bits, want_dt);
-  };
+  const bool alone = s->nb[0] * s->nb[1] * s->nb[2] == 1;      // the block owns every face of the domain: ghost copies written by the update itself
+  auto prim = [&](int want_dt) { LaunchScope ls(s, gx::KC_TCOND); s->K->tc_prim(s->A, c.mhd, s->U, s->PT, &s->dscal->tc_bits, want_dt, s->stream); };
+  auto update = [&](double dts) { LaunchScope ls(s, gx::KC_TCOND); s->K->tc_update(s->A, t, alone ? 1 : 0, s->PT, s->U, dts, s->stream); };
   // get_dt_cond (:78-110)
-  CUDA_TRY(cudaMemsetAsync(&s->dscal->tc_bits, 0x7f, sizeof(unsigned long long), s->stream));
   prim(1);
   if (s->comm && s->nranks > 1) NCCL_TRY(g_nccl.AllReduce(&s->dscal->tc_bits, &s->dscal->tc_bits, 1, ncclUint64, ncclMin, s->comm, s->stream));
   CUDA_TRY(cudaMemcpyAsync(&s->hscal->tc_bits, &s->dscal->tc_bits, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
@@ -857,8 +882,8 @@ static int thermal_conduction(gx_solver* s, double dt_cfl) {
     double dts;
     if (SuperStep) dts = dt_cond * fstep * gxtc::substep(n, Nsteps, 0.01) / t.Psc / c.rsc;                                 // :732
     else dts = dt_hydro / (double)Nsteps / t.Psc / c.rsc;
-    { LaunchScope ls(s, gx::KC_TCOND); gxtc::k_tc_update<<<gu, 128, 0, s->stream>>>(g, s->A.phys, t, s->PT, s->U, dts); }
-    int rc = thermal_bounds(s); if (rc) return rc;
+    update(dts);
+    if (!alone) { int rc = thermal_bounds(s); if (rc) return rc; }
     if (n < Nsteps) prim(0);                         // calcprim (:764); after the last substep the caller's calcprim pass does it
   }
   CUDA_TRY(cudaGetLastError());

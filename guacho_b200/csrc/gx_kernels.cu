@@ -9,6 +9,7 @@
 //   k_update    : step + flux_cd_update + source  src/hydro_solver.f90:77-127,
 //                 src/flux_cd_module.f90:285-323, src/sources.f90:124-220
 //   k_viscous   : viscous_copy  src/hydro_solver.f90:47-65
+#include <algorithm>
 #include "gx_kernels.cuh"
 #include "gx_split.cuh"
 
@@ -418,6 +419,9 @@ static int l_riemann_points(const Phys& P, int solver, int n, const double* wl, 
 }
 
 // ---------------------------------------------------------------------------
+#include "gx_thermal.cuh"          // thermal conduction kernels, compiled in this flavour
+
+// ---------------------------------------------------------------------------
 // launchers
 static inline dim3 grid_for(int nxr, int nyr, int nzr, int bx) { return dim3((unsigned)((nxr + bx - 1) / bx), (unsigned)nyr, (unsigned)nzr); }
 
@@ -535,7 +539,26 @@ static void l_bupdate(const StepArgs& A, double dt, const double* Ub, const doub
   else k_bupdate<false><<<grid, block, 0, s>>>(A, dtdx, dtdy, dtdz, Ub, E, dst, dtmin_bits);
 }
 
-static const KernelTable table = {l_calcprim, l_fluxes, l_efield, l_update, l_viscous, l_viscous2, l_stage, l_bupdate, l_riemann_points};
+static void l_tc_prim(const StepArgs& A, int mhd, const double* U, double* PT, unsigned long long* dt_bits, int want_dt, cudaStream_t s) {
+  const Grid& g = A.g;
+  // want_dt: the candidates are collected in 256 words (16 doubles apart) behind the two scratch variables, then folded into *dt_bits
+  unsigned long long* slots = reinterpret_cast<unsigned long long*>(PT + 2 * g.vs);
+  if (want_dt) cudaMemsetAsync(slots, 0x7f, 256 * 16 * sizeof(unsigned long long), s);
+  k_tc_prim<<<dim3((g.nx + 2 + 127) / 128, g.ny + 2, g.nz + 2), 128, 0, s>>>(g, A.phys, mhd, U, PT, slots, want_dt);
+  if (want_dt) k_tc_slots_min<<<1, 256, 0, s>>>(slots, dt_bits);
+}
+static void l_tc_update(const StepArgs& A, const TcPar& t, int fill, const double* PT, double* U, double dts, cudaStream_t s) {
+  const Grid& g = A.g;
+  const dim3 grid = grid_for(g.nx, g.ny, g.nz, 128);
+  if (fill) k_tc_update<true><<<grid, 128, 0, s>>>(g, A.phys, t, PT, U, dts);
+  else k_tc_update<false><<<grid, 128, 0, s>>>(g, A.phys, t, PT, U, dts);
+}
+static void l_tc_fill(const StepArgs& A, double* Aq, int edge, cudaStream_t s) {
+  const Grid& g = A.g;
+  k_tc_fill<<<dim3((std::max(g.nx + 2, g.ny) + 127) / 128, 2 * (g.ny + 2) + 4 * g.nz), 128, 0, s>>>(g, Aq, edge);
+}
+
+static const KernelTable table = {l_calcprim, l_fluxes, l_efield, l_update, l_viscous, l_viscous2, l_stage, l_bupdate, l_tc_prim, l_tc_update, l_tc_fill, l_riemann_points};
 
 }  // namespace GX_NS
 

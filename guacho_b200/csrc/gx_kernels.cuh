@@ -49,6 +49,18 @@ struct StepArgs {
   const double* W0;        // background primitives of the split-all solver (src/globals.f90:42 primit0; gx_set_background), else null
 };
 
+// thermal conduction (src/thermal_cond.f90): what the substep kernels read besides the grid
+struct TcPar {
+  int mode;                  // GX_TC_ISOTROPIC | GX_TC_ANISOTROPIC
+  int sat;                   // tc_saturation
+  int mhd;
+  double dxr, dyr, dzr;      // dx*rsc, dy*rsc, dz*rsc (the reference divides by the product)
+  double idxr, idyr, idzr;   // their reciprocals (production kernels)
+  double dx, dy, dz, idx, idy, idz;
+  double vsc, sqrt_vsc2;     // parameters.f90:167 ; sqrt(vsc2) as heatfluxes spells it (:213)
+  double Psc, rhosc, bsc2;   // Psc = rhosc*vsc2 (:168) ; bsc**2
+};
+
 // classes for the per-kernel timing table (gx_kernel_time_ms)
 enum { KC_FLUX = 0, KC_UPDATE = 1, KC_EFIELD = 2, KC_PRIM = 3, KC_BC = 4, KC_XPOSE = 5, KC_VISC = 6, KC_STAGE1 = 7, KC_STAGE2 = 8, KC_BUPDATE = 9, KC_TCOND = 10, KC_COUNT = 11 };
 
@@ -72,6 +84,12 @@ struct KernelTable {
   // flux-CD: dst(B) = Ub(B) - dt*curl E (central differences); want_cfl: CFL minimum of dst
   void (*bupdate)(const StepArgs&, double dt, const double* Ub, const double* E, double* dst,
                   unsigned long long* dtmin_bits, int want_cfl, cudaStream_t);
+  // thermal conduction (gx_thermal.cuh): pressure + temperature over 0..n+1 (+ Spitzer time-scale candidates); one substep of
+  // u(5) over the physical cells (fill: the block owns the whole domain, ghost copies written by the update); the zero-gradient
+  // ghost layer of u(5) after an exchange
+  void (*tc_prim)(const StepArgs&, int mhd, const double* U, double* PT, unsigned long long* dt_bits, int want_dt, cudaStream_t);
+  void (*tc_update)(const StepArgs&, const TcPar&, int fill, const double* PT, double* U, double dts, cudaStream_t);
+  void (*tc_fill)(const StepArgs&, double* A, int edge, cudaStream_t);
   // per-interface flux of n (rotated) primitive state pairs [n][8] (gx_riemann_flux)
   int (*riemann_points)(const gxp::Phys&, int solver, int n, const double* wl, const double* wr, double* ff, int* err, cudaStream_t);
 };
