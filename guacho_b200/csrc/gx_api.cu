@@ -74,6 +74,8 @@ struct gx_solver {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t cstream = nullptr;                             // halo push stream (overlaps the interior launches)
+  cudaStream_t xstream = nullptr;                             // PCIe copies of the layout conversion (upload_aos / download_aos)
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_xpose[2] = {nullptr, nullptr};
   cudaEvent_t ev_bnd = nullptr, ev_comm = nullptr;
   bool overlap = false;                                       // z slabs + peer push: boundary-first launches, exchange on cstream
   double *U = nullptr, *UP = nullptr, *W = nullptr, *F = nullptr, *E = nullptr, *Temp = nullptr, *T = nullptr;
@@ -359,32 +361,64 @@ static void launch_coolingh(gx_solver* s, double dt_cfl) {
 }
 
 // ---------------------------------------------------------------------------
+// Layout conversion pipeline: the staging area is used as two halves; PCIe copies run on a copy stream, the transposes on the
+// solver's stream, chained by events, so the copy of chunk c+1 overlaps the transpose of chunk c (round 1 synchronised the host
+// after every chunk).  The PCIe copy (1.1 GB at ~50 GB/s for 256^3) remains what the conversion costs.
+static int xfer_setup(gx_solver* s) {
+  if (s->xstream) return GX_OK;
+  CUDA_TRY(cudaStreamCreateWithFlags(&s->xstream, cudaStreamNonBlocking));
+  for (int h = 0; h < 2; ++h) {
+    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_copy[h], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_xpose[h], cudaEventDisableTiming));
+  }
+  return GX_OK;
+}
 static int upload_aos(gx_solver* s, const double* host, double* soa, int nvar) {
   const Grid& g = s->A.g;
+  int rc = xfer_setup(s); if (rc) return rc;
   const size_t plane = (size_t)nvar * (g.nx + 4) * (g.ny + 4);
-  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(g.nz + 4, s->stage_doubles / plane));
-  for (int k0 = 0; k0 < g.nz + 4; k0 += chunk) {
-    const int nk = std::min(chunk, g.nz + 4 - k0);
-    CUDA_TRY(cudaMemcpyAsync(s->stage, host + plane * k0, plane * nk * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    LaunchScope ls(s, gx::KC_XPOSE);
-    k_aos_to_soa<<<dim3((g.nx + 4 + 127) / 128, g.ny + 4, nk), 128, 0, s->stream>>>(g, nvar, s->stage, soa, k0, nk);
+  const size_t half = s->stage_doubles / 2;
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(g.nz + 4, half / plane));
+  CUDA_TRY(cudaEventRecord(s->ev_xpose[0], s->stream));          // the copy stream starts after whatever the solver's stream was doing
+  CUDA_TRY(cudaStreamWaitEvent(s->xstream, s->ev_xpose[0], 0));
+  int c = 0;
+  for (int k0 = 0; k0 < g.nz + 4; k0 += chunk, ++c) {
+    const int nk = std::min(chunk, g.nz + 4 - k0), h = c & 1;
+    double* st = s->stage + (size_t)h * half;
+    if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(s->xstream, s->ev_xpose[h], 0));      // the transpose that read this half (chunk c-2) is done
+    CUDA_TRY(cudaMemcpyAsync(st, host + plane * k0, plane * nk * sizeof(double), cudaMemcpyHostToDevice, s->xstream));
+    CUDA_TRY(cudaEventRecord(s->ev_copy[h], s->xstream));
+    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_copy[h], 0));
+    {
+      LaunchScope ls(s, gx::KC_XPOSE);
+      k_aos_to_soa<<<dim3((g.nx + 4 + 127) / 128, g.ny + 4, nk), 128, 0, s->stream>>>(g, nvar, st, soa, k0, nk);
+    }
+    CUDA_TRY(cudaEventRecord(s->ev_xpose[h], s->stream));
   }
   CUDA_TRY(cudaGetLastError());
   return GX_OK;
 }
 static int download_aos(gx_solver* s, const double* soa, double* host, int nvar) {
   const Grid& g = s->A.g;
+  int rc = xfer_setup(s); if (rc) return rc;
   const size_t plane = (size_t)nvar * (g.nx + 4) * (g.ny + 4);
-  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(g.nz + 4, s->stage_doubles / plane));
-  for (int k0 = 0; k0 < g.nz + 4; k0 += chunk) {
-    const int nk = std::min(chunk, g.nz + 4 - k0);
+  const size_t half = s->stage_doubles / 2;
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(g.nz + 4, half / plane));
+  int c = 0;
+  for (int k0 = 0; k0 < g.nz + 4; k0 += chunk, ++c) {
+    const int nk = std::min(chunk, g.nz + 4 - k0), h = c & 1;
+    double* st = s->stage + (size_t)h * half;
+    if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_copy[h], 0));        // the copy that read this half (chunk c-2) is done
     {
       LaunchScope ls(s, gx::KC_XPOSE);
-      k_soa_to_aos<<<dim3((g.nx + 4 + 127) / 128, g.ny + 4, nk), 128, 0, s->stream>>>(g, nvar, soa, s->stage, k0, nk);
+      k_soa_to_aos<<<dim3((g.nx + 4 + 127) / 128, g.ny + 4, nk), 128, 0, s->stream>>>(g, nvar, soa, st, k0, nk);
     }
-    CUDA_TRY(cudaMemcpyAsync(host + plane * k0, s->stage, plane * nk * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    CUDA_TRY(cudaStreamSynchronize(s->stream));   // staging buffer is reused by the next chunk
+    CUDA_TRY(cudaEventRecord(s->ev_xpose[h], s->stream));
+    CUDA_TRY(cudaStreamWaitEvent(s->xstream, s->ev_xpose[h], 0));
+    CUDA_TRY(cudaMemcpyAsync(host + plane * k0, st, plane * nk * sizeof(double), cudaMemcpyDeviceToHost, s->xstream));
+    CUDA_TRY(cudaEventRecord(s->ev_copy[h], s->xstream));
   }
+  CUDA_TRY(cudaStreamSynchronize(s->xstream));                    // the host array is complete; the staging halves are free again
   CUDA_TRY(cudaGetLastError());
   return GX_OK;
 }
@@ -758,6 +792,7 @@ int gx_destroy(gx_solver* s) {
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->cstream) cudaStreamSynchronize(s->cstream);
+  if (s->xstream) cudaStreamSynchronize(s->xstream);
   if (s->p2p && s->comm && g_nccl.ok) {          // nobody may unmap or free while a neighbour can still push into these arrays
     g_nccl.AllReduce(s->flags + FL_WORDS - 1, s->flags + FL_WORDS - 1, 1, ncclUint32, ncclSum, s->comm, s->stream);
     cudaStreamSynchronize(s->stream);
@@ -780,6 +815,8 @@ int gx_destroy(gx_solver* s) {
   if (s->ev_bnd) cudaEventDestroy(s->ev_bnd);
   if (s->ev_comm) cudaEventDestroy(s->ev_comm);
   if (s->cstream) cudaStreamDestroy(s->cstream);
+  for (int h = 0; h < 2; ++h) { if (s->ev_copy[h]) cudaEventDestroy(s->ev_copy[h]); if (s->ev_xpose[h]) cudaEventDestroy(s->ev_xpose[h]); }
+  if (s->xstream) cudaStreamDestroy(s->xstream);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
   return GX_OK;
