@@ -1265,8 +1265,9 @@ int gx_comm_attach(gx_solver* s, const void* idp, int32_t nbytes, int32_t rank, 
          cudaIpcGetMemHandle(&mine.h[3], s->flags) == cudaSuccess;
     if (ok && s->E) { ok = cudaIpcGetMemHandle(&mine.h[2], s->E) == cudaSuccess; mine.have_e = 1; }
     // every rank must take the same branch below: agree on `ok` first (min over ranks)
-    int* d_ok = nullptr; Pack* d_pk = nullptr;               // d_pk[0] = mine, [1] = from lo, [2] = from hi
-    if (cudaMalloc((void**)&d_ok, sizeof(int)) != cudaSuccess || cudaMalloc((void**)&d_pk, 3 * sizeof(Pack)) != cudaSuccess) return fail(GX_ENOMEM, "peer link buffers");
+    struct DevTmp { void* p = nullptr; ~DevTmp() { if (p) cudaFree(p); } } t_ok, t_pk;   // freed on every exit path
+    if (cudaMalloc(&t_ok.p, sizeof(int)) != cudaSuccess || cudaMalloc(&t_pk.p, 3 * sizeof(Pack)) != cudaSuccess) { cudaGetLastError(); return fail(GX_ENOMEM, "peer link buffers"); }
+    int* d_ok = (int*)t_ok.p; Pack* d_pk = (Pack*)t_pk.p;    // d_pk[0] = mine, [1] = from lo, [2] = from hi
     int okv = ok ? 1 : 0;
     CUDA_TRY(cudaMemcpy(d_ok, &okv, sizeof okv, cudaMemcpyHostToDevice));
     NCCL_TRY(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, s->comm, s->stream));
@@ -1312,7 +1313,6 @@ int gx_comm_attach(gx_solver* s, const void* idp, int32_t nbytes, int32_t rank, 
         CUDA_TRY(cudaEventCreateWithFlags(&s->ev_comm, cudaEventDisableTiming));
       }
     }
-    cudaFree(d_ok); cudaFree(d_pk);
   }
   return GX_OK;
 }
