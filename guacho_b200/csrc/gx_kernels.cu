@@ -420,6 +420,7 @@ static int l_riemann_points(const Phys& P, int solver, int n, const double* wl, 
 
 // ---------------------------------------------------------------------------
 #include "gx_thermal.cuh"          // thermal conduction kernels, compiled in this flavour
+#include "gx_cooling.cuh"          // COOL_H
 
 // ---------------------------------------------------------------------------
 // launchers
@@ -539,6 +540,10 @@ static void l_bupdate(const StepArgs& A, double dt, const double* Ub, const doub
   else k_bupdate<false><<<grid, block, 0, s>>>(A, dtdx, dtdy, dtdz, Ub, E, dst, dtmin_bits);
 }
 
+static void l_coolingh(const StepArgs& A, int mhd, double dt_seconds, double* U, cudaStream_t s) {
+  const Grid& g = A.g;
+  k_coolingh<<<grid_for(g.nx, g.ny, g.nz, 128), 128, 0, s>>>(g, A.phys, mhd, dt_seconds, U);
+}
 static void l_tc_prim(const StepArgs& A, int mhd, const double* U, double* PT, unsigned long long* dt_bits, int want_dt, cudaStream_t s) {
   const Grid& g = A.g;
   // want_dt: the candidates are collected in 256 words (16 doubles apart) behind the two scratch variables, then folded into *dt_bits
@@ -558,7 +563,7 @@ static void l_tc_fill(const StepArgs& A, double* Aq, int edge, cudaStream_t s) {
   k_tc_fill<<<dim3((std::max(g.nx + 2, g.ny) + 127) / 128, 2 * (g.ny + 2) + 4 * g.nz), 128, 0, s>>>(g, Aq, edge);
 }
 
-static const KernelTable table = {l_calcprim, l_fluxes, l_efield, l_update, l_viscous, l_viscous2, l_stage, l_bupdate, l_tc_prim, l_tc_update, l_tc_fill, l_riemann_points};
+static const KernelTable table = {l_calcprim, l_fluxes, l_efield, l_update, l_viscous, l_viscous2, l_stage, l_bupdate, l_tc_prim, l_tc_update, l_tc_fill, l_coolingh, l_riemann_points};
 
 }  // namespace GX_NS
 

@@ -112,8 +112,15 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, int parity) {
 #ifndef GX_STAGE_TY2
 #define GX_STAGE_TY2 11
 #endif
-#ifndef GX_STAGE_TYP                 // tile rows of the kernels that carry passive scalars (more variables per staged cell)
-#define GX_STAGE_TYP 7
+#ifndef GX_STAGE_TYP1                // tile rows of the kernels that carry passive scalars (more variables per staged cell): first-order stage
+#define GX_STAGE_TYP1 11             // (3 ring slots of 13 variables: 12 warps fit.  EXO 400x100x400: 1.81 ms against 1.89 with 7 rows, 1.97 with 10)
+#endif
+#ifndef GX_STAGE_TYP2                // ... second-order stage (5 ring slots of 10 variables: 8 rows would fit, but 9 warps are capped at 168 registers
+#define GX_STAGE_TYP2 7              //     like 12 and the kernel spills: 3.83 ms against 2.56)
+#endif
+#ifndef GX_STAGE_CONVERT_EARLY       // 1: the next plane is converted to primitives BEFORE the z solve (between the arrive and the wait of the
+#define GX_STAGE_CONVERT_EARLY 0     //    XY hand-over: more slack for warps that run ahead) instead of at the end of the plane.  Measured at 256^3:
+                                     //    stage 1 1.313 vs 1.301 ms, stage 2 1.742 vs 1.694 ms — rejected
 #endif
 #ifndef GX_STAGE_MINB1               // resident CTAs per SM the first-order headline kernel is compiled for (register cap = 64 K / threads)
 #define GX_STAGE_MINB1 1
@@ -127,7 +134,7 @@ struct StageGeom {
   static constexpr int NQ = NQ_, H = ORDER_, NCF = NCF_, NPAS = NPAS_;
   static constexpr int NU = NQ + NPAS;           // advected variables: dynamic + passive scalars
   static constexpr int NV = NU + NCF;            // staged per cell: primitives, passives (+ signal speeds, first-order stage)
-  static constexpr int TX = 32, TY = NPAS_ ? GX_STAGE_TYP : ((ORDER_ == 1) ? GX_STAGE_TY1 : GX_STAGE_TY2);
+  static constexpr int TX = 32, TY = NPAS_ ? ((ORDER_ == 1) ? GX_STAGE_TYP1 : GX_STAGE_TYP2) : ((ORDER_ == 1) ? GX_STAGE_TY1 : GX_STAGE_TY2);
   static constexpr int NW = TY + 1, NT = NW * 32;
   static constexpr int HX = 2;                   // x halo of the staged frame: 2 for both orders, so that every staged row starts on an
                                                  // even element (16-byte aligned box start: a TMA tile load faults on less)
@@ -422,6 +429,7 @@ k_stage(const StepArgs A, const StageDt sdt, const double* __restrict__ S, const
         gather<1, LIM, ORDER, NQ, NU, PC, PRE>(c - 2 * CX, c - CX, c, c + CX, wl, wr, csl, csr);
         if (NPAS) { pa = c - 2 * CX; pb = c - CX; pc = c; pd = c + CX; }
       } else {
+        if (GX_STAGE_CONVERT_EARLY && k < kend) { wait_load(sload, lpar); convert(sload); }
         const double* cm = (ORDER == 2) ? ring + slot_add(sk, NSLOT - 1) * G::PLANE + cidx : pk + cidx;
         const double* cp1 = ring + slot_add(sk, 1) * G::PLANE + cidx;
         const double* cp2 = (ORDER == 2) ? ring + slot_add(sk, 2) * G::PLANE + cidx : cp1;
@@ -562,13 +570,14 @@ k_stage(const StepArgs A, const StageDt sdt, const double* __restrict__ S, const
         for (int q = 0; q < NU; ++q) hprev[q] = h[q];
       }
     }
+    if (GX_STAGE_CONVERT_EARLY && !main_warp && k < kend) { wait_load(sload, lpar); convert(sload); }
     if (!main_warp && xy) {                               // the closing warp reads no fluxes; it keeps in step with the planes
       mbar_wait(bar_xy, it & 1);
       if (TMA) fence_proxy_async();
       mbar_arrive(bar_free);
     }
     if (xy) ++it;
-    if (k < kend) { wait_load(sload, lpar); convert(sload); }    // next plane -> primitives (own cells)
+    if (!GX_STAGE_CONVERT_EARLY && k < kend) { wait_load(sload, lpar); convert(sload); }    // next plane -> primitives (own cells)
     if (TMA && !xy) { fence_proxy_async(); __syncthreads(); }    // leading plane: its z solves are done before the next tile load (no FREE phase yet)
   }
   __syncthreads();
