@@ -190,6 +190,51 @@ __global__ void k_bc_face(Grid g, int nvar, double* __restrict__ A, int dir, int
   }
 }
 
+// All faces of a block that has no neighbours in ONE launch over its ghost shell (nl layers).  The reference fills the faces one
+// after the other (periodic copies, then closed walls, then outflow: boundaries.f90:101-242, 316-505), every pass over the full
+// transverse extent including the ghost layers already filled, so edge and corner ghosts end up with the COMPOSITION of the
+// per-direction maps (wrap: dst -/+ n; mirror: 1 - dst | 2n + 1 - dst) whatever the order — which is what a thread evaluates here.
+// mode[2*dir+side]: 0 leave alone (user boundary, or a direction the fused kernels wrap in their loaders), 1 periodic wrap,
+// 2 mirror; neg[2*dir+side]: variable whose sign flips across that face (closed walls), -1 for none.  Sources are never
+// destinations: a source has every index either inside the block or in a direction that is left alone.
+struct ShellBc { int mode[6], neg[6]; };
+__global__ void __launch_bounds__(128) k_bc_shell(Grid g, int nvar, double* __restrict__ A, int nl, ShellBc bc) {
+  const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const int ex = g.nx + 2 * nl, ey = g.ny + 2 * nl;
+  int r = (int)blockIdx.y, i, j, k;
+  if (r < 2 * nl * ey) {                                   // the 2 nl z planes: rows along x
+    const int pl = r / ey; j = r - pl * ey + 1 - nl; k = pl < nl ? pl + 1 - nl : g.nz + 1 + (pl - nl); i = t + 1 - nl; if (t >= ex) return;
+  } else if ((r -= 2 * nl * ey) < 2 * nl * g.nz) {         // the 2 nl y planes between them: rows along x
+    const int pl = r / g.nz; k = r - pl * g.nz + 1; j = pl < nl ? pl + 1 - nl : g.ny + 1 + (pl - nl); i = t + 1 - nl; if (t >= ex) return;
+  } else {                                                 // the 2 nl x planes: rows along y
+    r -= 2 * nl * g.nz; const int pl = r / g.nz; k = r - pl * g.nz + 1; i = pl < nl ? pl + 1 - nl : g.nx + 1 + (pl - nl); j = t + 1; if (t >= g.ny) return;
+  }
+  const int n[3] = {g.nx, g.ny, g.nz};
+  int d[3] = {i, j, k}, sidx[3] = {i, j, k}, flip0 = -1, flip1 = -1, flip2 = -1;
+  bool moved = false;
+#pragma unroll
+  for (int dir = 0; dir < 3; ++dir) {
+    const int side = d[dir] < 1 ? 0 : (d[dir] > n[dir] ? 1 : -1);
+    if (side < 0) continue;
+    const int m = bc.mode[2 * dir + side];
+    if (m == 1) { sidx[dir] = side == 0 ? d[dir] + n[dir] : d[dir] - n[dir]; moved = true; }
+    else if (m == 2) {
+      sidx[dir] = side == 0 ? 1 - d[dir] : 2 * n[dir] + 1 - d[dir]; moved = true;
+      const int nv = bc.neg[2 * dir + side];
+      if (dir == 0) flip0 = nv; else if (dir == 1) flip1 = nv; else flip2 = nv;
+    }
+  }
+  if (!moved) return;
+  const long long cd = g.idx(i, j, k), cs = g.idx(sidx[0], sidx[1], sidx[2]);
+  for (int q = 0; q < nvar; ++q) {
+    double v = A[q * g.vs + cs];
+    if (q == flip0) v = -v;
+    if (q == flip1) v = -v;
+    if (q == flip2) v = -v;
+    A[q * g.vs + cd] = v;
+  }
+}
+
 // pack / unpack a box [lo,hi] (Fortran indices, inclusive) of nvar variables to/from a contiguous buffer
 struct Box { int lo[3], hi[3]; };
 __global__ void k_pack(Grid g, int nvar, double* A, double* buf, Box bx, int unpack_flag) {
@@ -453,6 +498,28 @@ static void launch_bc_face(gx_solver* s, double* A, int nvar, int dir, int side,
 // download entry points use, so that gx_get_state / gx_get_up are NOT collective calls.
 static int apply_boundaries(gx_solver* s, double* A, int nvar, int nl, int kind, bool skip_wrapped = false, cudaStream_t st = nullptr,
                             bool local_only = false) {
+  if (s->nb[0] * s->nb[1] * s->nb[2] == 1 && !getenv("GX_NO_BC_SHELL")) {       // no neighbours: the whole ghost shell in one launch
+    ShellBc bc;
+    bool any = false;
+    for (int dir = 0; dir < 3; ++dir)
+      for (int side = 0; side < 2; ++side) {
+        int m = 0, neg = -1;
+        if (s->periodic[dir]) m = (skip_wrapped && s->A.wrap[dir]) ? 0 : 1;
+        else if (s->bc[dir][side] == GX_BC_OUTFLOW) m = 2;
+        else if (s->bc[dir][side] == GX_BC_CLOSED) { m = 2; neg = kind == 0 ? 1 + dir : (dir == 2 ? -1 : dir); }
+        bc.mode[2 * dir + side] = m; bc.neg[2 * dir + side] = neg;
+        any = any || m != 0;
+      }
+    if (any) {
+      const Grid& g = s->A.g;
+      LaunchScope ls(s, gx::KC_BC);
+      const dim3 grid((std::max(g.nx + 2 * nl, g.ny) + 127) / 128, 2 * nl * (g.ny + 2 * nl) + 4 * nl * g.nz);
+      k_bc_shell<<<grid, 128, 0, st ? st : s->stream>>>(g, nvar, A, nl, bc);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return fail(GX_ECUDA, "boundary kernel launch: %s", cudaGetErrorString(e));
+    }
+    return GX_OK;
+  }
   for (int dir = 0; dir < 3; ++dir) {
     if (s->nb[dir] == 1 && s->periodic[dir]) {            // neighbour is the block itself
       if (skip_wrapped && s->A.wrap[dir]) continue;       // the fused kernels wrap their reads instead

@@ -66,16 +66,11 @@ __device__ double cool_aloss(double X1, double DEN, double DH0, double TE0) {   
   }
   return ECOLL + EION + (EREC + 7.033 * (EOI + EOII)) * (1. - FR) + EQUIL * FR;
 }
-// atomic(dt,uu,tau,radphi), dif_rad = .false. (:259-371), over the physical cells (coolingh, :41-67)
-__global__ void __launch_bounds__(128) k_coolingh(Grid g, gxp::Phys P, int mhd, double dt, double* __restrict__ U) {
-  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) + 1, j = (int)blockIdx.y + 1, k = (int)blockIdx.z + 1;
-  if (i > g.nx) return;
-  const long long c = g.idx(i, j, k), vs = g.vs;
+// atomic(dt,uu,tau,radphi), dif_rad = .false. (:259-371) on one cell: uu = the dynamic variables, un = the neutral H density
+// uu(neqdyn+1); returns the new energy uu(5) and neutral density
+__device__ __forceinline__ void cool_cell(const gxp::Phys& P, int mhd, double dt, const double (&uu)[8], double un, double& e5_out, double& un_out) {
   const double xi = 1.e-4, boltzm = 1.3807e-16;
-  double uu[8], prim[8], T;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) uu[q] = (q < g.neqdyn) ? U[q * vs + c] : 0.0;
-  const double un = U[(long long)g.neqdyn * vs + c];            // neutral H density, uu(neqdyn+1)
+  double prim[8], T;
   if (mhd) gxp::u2prim<true, true>(P, uu, prim, un, T); else gxp::u2prim<false, true>(P, uu, prim, un, T);
   const double col = cool_colf(T);
   const double rec = cool_alpha(T);
@@ -97,11 +92,26 @@ __global__ void __launch_bounds__(128) k_coolingh(Grid g, gxp::Phys P, int mhd, 
   t1 = fmax(t1, 0.1 * T);
   t1 = fmin(t1, 10. * T);
   const double un1 = y1 * uu[0];
-  U[(long long)g.neqdyn * vs + c] = un1;
   double e5 = P.cv * (2. * uu[0] - un1) * t1 / P.Tempsc + 0.5 * prim[0] * (prim[1] * prim[1] + prim[2] * prim[2] + prim[3] * prim[3]);
   if (mhd) e5 = e5 + 0.5 * (prim[5] * prim[5] + prim[6] * prim[6] + prim[7] * prim[7]);
+  e5_out = e5; un_out = un1;
+}
+// coolingh (:41-67): atomic over the physical cells
+__global__ void __launch_bounds__(128) k_coolingh(Grid g, gxp::Phys P, int mhd, double dt, double* __restrict__ U) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x) + 1, j = (int)blockIdx.y + 1, k = (int)blockIdx.z + 1;
+  if (i > g.nx) return;
+  const long long c = g.idx(i, j, k), vs = g.vs;
+  double uu[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) uu[q] = (q < g.neqdyn) ? U[q * vs + c] : 0.0;
+  const double un = U[(long long)g.neqdyn * vs + c];            // neutral H density, uu(neqdyn+1)
+  double e5, un1;
+  cool_cell(P, mhd, dt, uu, un, e5, un1);
+  U[(long long)g.neqdyn * vs + c] = un1;
   U[4 * vs + c] = e5;
 }
+// (Measured and rejected: coolingh as the epilogue of the viscous_copy stencil pass — 2.12 ms against 0.59 + 1.01 ms for the two
+// kernels at EXO's 400x100x400: 70 stencil loads in front of a long dependent transcendental chain at 72 registers hide nothing.)
 #undef GX_POW
 #undef GX_POW10
 #undef GX_POWHALF
