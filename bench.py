@@ -326,9 +326,9 @@ def run_tcond(args, rank, local_rank, world):
     zones = p.nx * p.ny * p.nz
     step_ms = ms / args.steps
     tc_ms = ktimes["tcond"][0] / nprof
-    # per substep: k_tc_update reads p, T, rho and reads + writes u(5) (5 doubles); k_tc_prim reads the 8 dynamic variables and
-    # writes p, T (10 doubles); the first k_tc_prim of a call (dt_cond) replaces the one after the last substep
-    tc_bytes = (40.0 + 80.0) * zones * (sub / nprof)
+    # one block, isotropic: ONE marching kernel per substep reads the dynamic variables once and writes u(5): 8*(neqdyn + 1) B
+    tc_bytes_zone = 8.0 * (p.neqdyn + 1)
+    tc_bytes = tc_bytes_zone * zones * (sub / nprof)
     line = {"metric": "MHD zone-updates/s with thermal conduction (HLLD + flux-CD + isotropic saturated Spitzer conduction, super-time-stepping, FP64)",
             "value": zones * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -336,8 +336,8 @@ def run_tcond(args, rank, local_rank, world):
                        "substeps_last_step": nsub, "dt_cond_s": dt_cond, "l2": "working set exceeds the 126 MB L2; no flush needed"},
             "clocks": clocks, "gpu_launches": int(l1 - l0),
             "roofline": {"bound": "hbm", "achieved": tc_bytes / (tc_ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s", "frac": tc_bytes / (tc_ms * 1e-3) / 1e9 / peak_gbs, "traffic": None,
-                         "peak_source": peak_src, "kernel": "k_tc_update + k_tc_prim (thermal conduction substeps)", "ms_per_step": tc_ms,
-                         "substeps_per_step": sub / nprof, "algorithmic_bytes_per_zone_per_substep": 120.0,
+                         "peak_source": peak_src, "kernel": "k_tc_march (one launch per thermal-conduction substep) + k_tc_prim once per step (dt_cond)", "ms_per_step": tc_ms,
+                         "substeps_per_step": sub / nprof, "algorithmic_bytes_per_zone_per_substep": tc_bytes_zone,
                          "kernel_ms_per_step": {k: v[0] / nprof for k, v in ktimes.items() if v[1]}},
             "finite": finite, "last_dt": last_dt}
     print(json.dumps(line), flush=True)

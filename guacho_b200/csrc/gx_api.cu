@@ -890,10 +890,23 @@ static int thermal_conduction(gx_solver* s, double dt_cfl) {
   if (dt_cond < dt_hydro) gxtc::ST_steps(dt_hydro / dt_cond, Nsteps, fstep);
   else { SuperStep = false; fstep = dt_hydro / dt_cond; Nsteps = 1; }
   s->tc_dt_cond = dt_cond; s->tc_nsteps = Nsteps;
+  // isotropic conduction on a block without neighbours: one marching kernel per substep (k_tc_march), u(5) alternating between
+  // the energy array of u and the first scratch variable; everything else: k_tc_update / thermal_bounds / k_tc_prim
+  const bool march = alone && c.th_cond == GX_TC_ISOTROPIC && !getenv("GX_NO_TC_MARCH");
+  double* const e5u = s->U + 4 * g.vs;
+  double* e5in = e5u;
   for (int n = 1; n <= Nsteps; ++n) {
     double dts;
     if (SuperStep) dts = dt_cond * fstep * gxtc::substep(n, Nsteps, 0.01) / t.Psc / c.rsc;                                 // :732
     else dts = dt_hydro / (double)Nsteps / t.Psc / c.rsc;
+    if (march) {
+      double* e5out = e5in == e5u ? s->PT : e5u;
+      { LaunchScope ls(s, gx::KC_TCOND); s->K->tc_march(s->A, t, c.mhd, s->U, e5in, e5out, dts, s->stream); }
+      e5in = e5out;
+      if (n == Nsteps && e5in != e5u)                  // odd number of substeps: the result sits in the scratch variable (ghost layer included)
+        CUDA_TRY(cudaMemcpyAsync(e5u, e5in, (size_t)g.vs * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+      continue;
+    }
     update(dts);
     if (!alone) { int rc = thermal_bounds(s); if (rc) return rc; }
     if (n < Nsteps) prim(0);                         // calcprim (:764); after the last substep the caller's calcprim pass does it

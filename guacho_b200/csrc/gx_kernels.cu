@@ -558,12 +558,23 @@ static void l_tc_update(const StepArgs& A, const TcPar& t, int fill, const doubl
   if (fill) k_tc_update<true><<<grid, 128, 0, s>>>(g, A.phys, t, PT, U, dts);
   else k_tc_update<false><<<grid, 128, 0, s>>>(g, A.phys, t, PT, U, dts);
 }
+static void l_tc_march(const StepArgs& A, const TcPar& t, int mhd, const double* U, const double* E5in, double* E5out, double dts, cudaStream_t s) {
+  const Grid& g = A.g;
+  const int tiles = ((g.nx + TCM_TX - 1) / TCM_TX) * ((g.ny + TCM_TY - 1) / TCM_TY);
+  // planes per CTA: long marches (the prologue of a chunk costs two planes of conversions), but at least ~3 waves of resident CTAs
+  int chunks = std::max(1, std::min(g.nz / 16, (148 * 3 * 3 + tiles - 1) / tiles));
+  const int kz = (g.nz + chunks - 1) / chunks;
+  chunks = (g.nz + kz - 1) / kz;
+  const dim3 grid((g.nx + TCM_TX - 1) / TCM_TX, (g.ny + TCM_TY - 1) / TCM_TY, chunks), block(TCM_TX, TCM_TY);
+  if (mhd) k_tc_march<true><<<grid, block, 0, s>>>(g, A.phys, t, U, E5in, E5out, dts, kz);
+  else k_tc_march<false><<<grid, block, 0, s>>>(g, A.phys, t, U, E5in, E5out, dts, kz);
+}
 static void l_tc_fill(const StepArgs& A, double* Aq, int edge, cudaStream_t s) {
   const Grid& g = A.g;
   k_tc_fill<<<dim3((std::max(g.nx + 2, g.ny) + 127) / 128, 2 * (g.ny + 2) + 4 * g.nz), 128, 0, s>>>(g, Aq, edge);
 }
 
-static const KernelTable table = {l_calcprim, l_fluxes, l_efield, l_update, l_viscous, l_viscous2, l_stage, l_bupdate, l_tc_prim, l_tc_update, l_tc_fill, l_coolingh, l_riemann_points};
+static const KernelTable table = {l_calcprim, l_fluxes, l_efield, l_update, l_viscous, l_viscous2, l_stage, l_bupdate, l_tc_prim, l_tc_update, l_tc_fill, l_tc_march, l_coolingh, l_riemann_points};
 
 }  // namespace GX_NS
 

@@ -90,6 +90,8 @@ struct KernelTable {
   void (*tc_prim)(const StepArgs&, int mhd, const double* U, double* PT, unsigned long long* dt_bits, int want_dt, cudaStream_t);
   void (*tc_update)(const StepArgs&, const TcPar&, int fill, const double* PT, double* U, double dts, cudaStream_t);
   void (*tc_fill)(const StepArgs&, double* A, int edge, cudaStream_t);
+  // isotropic conduction, block without neighbours: one marching kernel per substep, u(5) from E5in to E5out (k_tc_march)
+  void (*tc_march)(const StepArgs&, const TcPar&, int mhd, const double* U, const double* E5in, double* E5out, double dts, cudaStream_t);
   // COOL_H (gx_cooling.cuh): atomic(dt, uu) over the physical cells (src/cooling_h.f90:41-67, 259-371)
   void (*coolingh)(const StepArgs&, int mhd, double dt_seconds, double* U, cudaStream_t);
   // per-interface flux of n (rotated) primitive state pairs [n][8] (gx_riemann_flux)

@@ -191,3 +191,104 @@ __global__ void __launch_bounds__(128) k_tc_fill(gx::Grid g, double* __restrict_
   if (si == i && sj == j && sk == k) return;
   A[g.idx(i, j, k)] = A[g.idx(si, sj, sk)];
 }
+
+// ---------------------------------------------------------------------------
+// One substep of ISOTROPIC conduction for a block that owns the whole domain, as ONE marching kernel: no pressure /
+// temperature arrays in HBM and every face flux evaluated once.  A CTA owns a 32 x 8 column of cells and marches along z.
+// Per plane a thread loads the conserved variables of its cell in the NEXT plane (+ one cell of that plane's halo ring),
+// converts them (u2prim: the reference's calcprim, restricted to what the fluxes read) and parks pressure, temperature and
+// density of the plane in shared memory; it evaluates the upper x and y face of its cell from the CURRENT plane's tile and
+// the upper z face from registers (the lower z face is the previous plane's upper one), hands the x / y fluxes over through
+// shared memory and updates u(5).  The 40 faces on the low x / y side of the tile are shared out to the first 40 threads.
+// u(5) is read from E5in and written to E5out (the halo cells of a tile belong to other CTAs, which may already have
+// updated them): the caller alternates the energy array of u and a scratch array.  Ghost copies of thermal_bounds as in
+// k_tc_update<FILL>.  Algorithmic traffic: neqdyn reads + 1 write per zone and substep (72 B; the two-kernel form moves 120).
+// Same arithmetic per face and per cell as heatfluxes / the update loop of thermal_conduction (:189-267, :749-757).
+constexpr int TCM_TX = 32, TCM_TY = 8, TCM_SX = TCM_TX + 2, TCM_SY = TCM_TY + 2, TCM_NT = TCM_TX * TCM_TY;
+#ifndef GX_TCM_MINB                  // resident CTAs per SM: latency-bound like k_tc_update — 4 (64 registers, a few spills): 4.47 ms for 9 substeps
+#define GX_TCM_MINB 4                // at 256^3, 3 (80 registers): 4.85, 2 (100): 6.42
+#endif
+template <bool MHD>
+__global__ void __launch_bounds__(TCM_NT, GX_TCM_MINB) k_tc_march(gx::Grid g, gxp::Phys P, gx::TcPar t, const double* __restrict__ U, const double* __restrict__ E5in,
+                                                         double* __restrict__ E5out, double dts, int kz) {
+  constexpr int TX = TCM_TX, TY = TCM_TY, SX = TCM_SX, SY = TCM_SY, NT = TCM_NT;
+  __shared__ double sT[2][SY][SX], sp[2][SY][SX], sr[2][SY][SX];
+  __shared__ double fx[TY][TX + 1], fy[TY + 1][TX];
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
+  const int i0 = 1 + (int)blockIdx.x * TX, j0 = 1 + (int)blockIdx.y * TY;
+  const int k0 = 1 + (int)blockIdx.z * kz, k1 = min(k0 + kz - 1, g.nz);
+  const int i = i0 + tx, j = j0 + ty;
+  const bool ok = i <= g.nx && j <= g.ny;
+  const long long vs = g.vs, sz = (long long)g.px * g.py;
+  // this thread's halo cell of a plane (tile-local coordinates; the four corners are never read): 2 x 32 + 2 x 8 = 80 cells
+  int hx = -1, hy = -1;
+  if (tid < TX) { hx = tid + 1; hy = 0; }
+  else if (tid < 2 * TX) { hx = tid - TX + 1; hy = SY - 1; }
+  else if (tid < 2 * TX + TY) { hx = 0; hy = tid - 2 * TX + 1; }
+  else if (tid < 2 * TX + 2 * TY) { hx = SX - 1; hy = tid - 2 * TX - TY + 1; }
+  // addresses clamped into the ghost layer (tiles may overhang the block; such cells are never used by a live update)
+  const long long own0 = g.idx(min(i, g.nx + 1), min(j, g.ny + 1), 0);
+  const long long halo0 = g.idx(min(i0 - 1 + max(hx, 0), g.nx + 1), min(j0 - 1 + max(hy, 0), g.ny + 1), 0);
+  auto prim_of = [&](long long c, double& pT, double& pp, double& pr, double& e5) {
+    double uu[8], w[8], T;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) uu[q] = (q < (MHD ? 8 : 5) && q != 4) ? U[q * vs + c] : 0.0;
+    uu[4] = e5 = E5in[c];
+    const double un = g.npas > 0 ? U[(long long)g.neqdyn * vs + c] : 0.0;
+    gxp::u2prim<MHD, true>(P, uu, w, un, T);
+    pT = T; pp = w[4]; pr = w[0];
+  };
+  auto stage_plane = [&](int k, int b, double& Tn, double& pn, double& rn, double& en) {      // plane k -> tile buffer b (+ own values)
+    const long long off = (long long)k * sz;
+    prim_of(own0 + off, Tn, pn, rn, en);
+    sT[b][ty + 1][tx + 1] = Tn; sp[b][ty + 1][tx + 1] = pn; sr[b][ty + 1][tx + 1] = rn;
+    if (hx >= 0) {
+      double hT, hp, hr, he;
+      prim_of(halo0 + off, hT, hp, hr, he);
+      sT[b][hy][hx] = hT; sp[b][hy][hx] = hp; sr[b][hy][hx] = hr;
+    }
+  };
+  // prologue: plane k0-1 (own column only: the first lower z flux) and plane k0 (tile)
+  double Tc, pc, rc, ec, Tn, pn, rn, en, zlo;
+  {
+    double Tm, pm, rm, em;
+    prim_of(own0 + (long long)(k0 - 1) * sz, Tm, pm, rm, em);
+    stage_plane(k0, 0, Tc, pc, rc, ec);
+    zlo = flux_iso(t, P, Tm, Tc, pm, pc, rm, rc, t.dzr, t.idzr);
+  }
+  __syncthreads();
+  int b = 0;
+#pragma unroll 1
+  for (int k = k0; k <= k1; ++k, b ^= 1) {
+    stage_plane(k + 1, b ^ 1, Tn, pn, rn, en);                       // next plane: conversion + tile for the next iteration
+    // upper x and y face of my cell, from the current plane's tile
+    fx[ty][tx + 1] = flux_iso(t, P, Tc, sT[b][ty + 1][tx + 2], pc, sp[b][ty + 1][tx + 2], rc, sr[b][ty + 1][tx + 2], t.dxr, t.idxr);
+    fy[ty + 1][tx] = flux_iso(t, P, Tc, sT[b][ty + 2][tx + 1], pc, sp[b][ty + 2][tx + 1], rc, sr[b][ty + 2][tx + 1], t.dyr, t.idyr);
+    if (tid < TY) {                                                  // low x side of the tile: face (i0-1 | i0) of row tid
+      fx[tid][0] = flux_iso(t, P, sT[b][tid + 1][0], sT[b][tid + 1][1], sp[b][tid + 1][0], sp[b][tid + 1][1], sr[b][tid + 1][0], sr[b][tid + 1][1], t.dxr, t.idxr);
+    } else if (tid < TY + TX) {                                      // low y side: face (j0-1 | j0) of column tid - TY
+      const int cx = tid - TY + 1;
+      fy[0][cx - 1] = flux_iso(t, P, sT[b][0][cx], sT[b][1][cx], sp[b][0][cx], sp[b][1][cx], sr[b][0][cx], sr[b][1][cx], t.dyr, t.idyr);
+    }
+    const double zhi = flux_iso(t, P, Tc, Tn, pc, pn, rc, rn, t.dzr, t.idzr);
+    __syncthreads();                                                 // fluxes of this plane and the next plane's tile are in place
+    if (ok) {
+      const long long c = own0 + (long long)k * sz;
+#if defined(GX_FLAVOUR_FAST)
+      const double v = ec - dts * ((fx[ty][tx + 1] - fx[ty][tx]) * t.idx + (fy[ty + 1][tx] - fy[ty][tx]) * t.idy + (zhi - zlo) * t.idz);
+#else
+      const double v = ec - dts * ((fx[ty][tx + 1] - fx[ty][tx]) / t.dx + (fy[ty + 1][tx] - fy[ty][tx]) / t.dy + (zhi - zlo) / t.dz);
+#endif
+      E5out[c] = v;
+      const int ex = i == 1 ? -1 : (i == g.nx ? 1 : 0), ey = j == 1 ? -1 : (j == g.ny ? 1 : 0), ez = k == 1 ? -1 : (k == g.nz ? 1 : 0);
+      if (ex | ey | ez) {
+        for (int a = 0; a <= (ez != 0); ++a)
+          for (int bb = 0; bb <= (ey != 0); ++bb)
+            for (int d = 0; d <= (ex != 0); ++d)
+              if (a | bb | d) E5out[c + (long long)(a * ez) * sz + (long long)(bb * ey) * g.px + d * ex] = v;
+      }
+    }
+    zlo = zhi; Tc = Tn; pc = pn; rc = rn; ec = en;
+    __syncthreads();                                                 // everyone has read fx / fy and tile b before the next plane overwrites them
+  }
+}
