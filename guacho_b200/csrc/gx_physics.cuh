@@ -325,6 +325,18 @@ __device__ __forceinline__ void reconstruct(double pll, double& pl, double& pr, 
   double dl = pl - pll;
   double dm = pr - pl;
   double dr = prr - pr;
+#if defined(GX_FLAVOUR_FAST) && !defined(GX_NO_MINMOD_HALF)
+  if (LIM == GX_LIMITER_MINMOD) {
+    // minmod(a, b) * 0.5 as  m * h  with m = the argument of smaller magnitude and h = 0.5 | 0 by the sign test: the same value
+    // (m * 0.5 is exact, m * 0 adds a zero), but the "or zero" select acts on one constant word instead of the two words of m
+    const double ml = (fabs(dl) < fabs(dm)) ? dl : dm, mr = (fabs(dm) < fabs(dr)) ? dm : dr;
+    const double hl = ((__double2hiint(dl) ^ __double2hiint(dm)) >= 0) ? 0.5 : 0.0;
+    const double hr = ((__double2hiint(dm) ^ __double2hiint(dr)) >= 0) ? 0.5 : 0.0;
+    pl = fma(ml, hl, pl);
+    pr = fma(-mr, hr, pr);
+    return;
+  }
+#endif
   double al = average<LIM>(dl, dm);
   double ar = average<LIM>(dm, dr);
   pl = pl + al * 0.5;
