@@ -155,6 +155,39 @@ def test_physical_boundaries(bc):
     assert rel_err_per_var(ug, uo).max() <= TOL
 
 
+@pytest.mark.parametrize("bcs", [(BC_CLOSED, BC_OUTFLOW, BC_PERIODIC), (BC_OUTFLOW, BC_CLOSED, BC_CLOSED), (BC_PERIODIC, BC_PERIODIC, BC_OUTFLOW)])
+@pytest.mark.parametrize("fused", [True, False])
+def test_ghost_shell_in_one_launch_equals_the_face_by_face_fills(bcs, fused, monkeypatch):
+    """A block without neighbours fills its whole ghost shell in one launch (k_bc_shell: the composition of the per-face maps);
+    the face-by-face kernels (what blocks with neighbours use around the exchange, and the reference's order: periodic copies,
+    closed walls, outflow) must leave the same arrays, ghost layers, edges and corners included — u (one layer) and up (two)."""
+    from guacho_b200.solver import Block
+    bx, by, bz = bcs
+    p = Params(nxtot=24, nytot=20, nztot=16, zmax=1.0, bc_left=bx, bc_right=bx, bc_bottom=by, bc_top=by, bc_out=bz, bc_in=bz,
+               eight_wave=not fused, enable_flux_cd=fused)          # the 8-wave source takes the pass-per-routine kernels
+    g = global_ic(p, "random")
+    out = {}
+    for shell in (True, False):
+        if shell:
+            monkeypatch.delenv("GX_NO_BC_SHELL", raising=False)
+        else:
+            monkeypatch.setenv("GX_NO_BC_SHELL", "1")
+        with Block(p) as b:
+            b.set_state(g)
+            t, it = 0.0, 1
+            for _ in range(2):
+                dt, _ = b.get_timestep(it, 10, t, 1e300)
+                b.tstep(dt); t += dt; it += 1
+            out[shell] = (b.get_state(), b.get_up())
+    assert np.array_equal(out[True][0][:, 1:-1, 1:-1, 1:-1], out[False][0][:, 1:-1, 1:-1, 1:-1])      # u: the layer boundaryI fills
+    assert np.array_equal(out[True][1], out[False][1])                                                  # up: both layers (boundaryII)
+    if BC_PERIODIC not in bcs:        # mirror-type walls: the oracle's sequential copies leave the same composition in edges and corners
+        o = oracle_from_ic(p, g)
+        o.advance(2)
+        ref = o.get_block(0, U)[:, 1:-1, 1:-1, 1:-1]
+        assert rel_err_per_var(out[True][0][:, 1:-1, 1:-1, 1:-1], ref).max() <= TOL
+
+
 @pytest.mark.parametrize("strict", [True, False])
 @pytest.mark.parametrize("solver,mhd,cd", [(SOLVER_HLLD, True, True), (SOLVER_HLLC, False, False)])
 def test_viscosity_on_the_fused_path_periodic(solver, mhd, cd, strict):

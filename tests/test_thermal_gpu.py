@@ -49,6 +49,32 @@ def test_thermal_conduction_mhd_outflow(mode, sat, strict):
     assert rel_err_per_var(ug, uo).max() <= TOL, rel_err_per_var(ug, uo)
 
 
+@pytest.mark.parametrize("sat", [False, True])
+def test_marching_kernel_and_the_two_kernel_substep_agree(sat, monkeypatch):
+    """One block, isotropic: k_tc_march (one launch per substep, every face flux once) against k_tc_update + k_tc_prim (what blocks
+    with neighbours and the anisotropic operator use) — the strict flavours evaluate the same expressions on the same values."""
+    from guacho_b200.solver import Block
+    out = {}
+    for strict in (True, False):
+        p = Params(nxtot=40, nytot=20, nztot=24, zmax=1.0, th_cond=TC_ISOTROPIC, tc_saturation=sat, strict_fp=strict, **tc_scalings(), **OUTFLOW)
+        g = global_ic(p, "random")
+        for march in (True, False):
+            if march:
+                monkeypatch.delenv("GX_NO_TC_MARCH", raising=False)
+            else:
+                monkeypatch.setenv("GX_NO_TC_MARCH", "1")
+            with Block(p) as b:
+                b.set_state(g)
+                t, it = 0.0, 11
+                for _ in range(2):
+                    dt, _ = b.get_timestep(it, 10, t, 1e300)
+                    b.tstep(dt); t += dt; it += 1
+                    assert b.tc_info()[1] > 1
+                out[(strict, march)] = interior(b.get_state())
+    assert np.array_equal(out[(True, True)], out[(True, False)])
+    assert rel_err_per_var(out[(False, True)], out[(False, False)]).max() <= TOL
+
+
 def test_thermal_conduction_single_substep_during_the_cfl_ramp():
     """dt_cond >= dt_hydro: SuperStep = .false., one substep of the hydro step (thermal_cond.f90:714-720)."""
     p = Params(nxtot=24, nytot=20, nztot=16, zmax=1.0, th_cond=TC_ISOTROPIC, **tc_scalings(), **OUTFLOW)
